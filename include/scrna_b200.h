@@ -1,0 +1,177 @@
+/* libscrna_b200 -- C ABI of the B200-native (sm_100a) scRNA clustering hot path.
+ *
+ * The reference (nicococo/scRNA) is pure Python and has NO FFI of its own: its hot
+ * path is reached through Python classes that delegate the arithmetic to scikit-learn / scipy /
+ * numpy.  Each entry point below therefore cites the reference call site (file:line under
+ * /root/reference, or SP/ = the installed scikit-learn / scipy the reference calls into) whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the reference
+ * would add.
+ *
+ * Conventions
+ *   - every function returns SCRNA_OK (0) or a negative SCRNA_ERR_* code; nothing throws;
+ *   - all data pointers are DEVICE pointers owned by the caller; the library never allocates;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call is
+ *     asynchronous on that stream and safe to capture in a CUDA graph;
+ *   - X is always genes x cells, row-major fp32, leading dimension `ldx` (elements, multiple of 4,
+ *     columns [n, ldx) zero-filled) -- the reference layout (abstract_clustering.py:28-29) narrowed
+ *     to fp32 storage;
+ *   - factors: gene factor G is g x kp row-major, cell factor C is kp x ldc row-major, with
+ *     kp = k rounded up to a multiple of 4 and padding rows/columns kept at zero.  Both exist as an
+ *     fp64 master (updated by the epilogues) and an fp32 shadow (read by the X sweeps);
+ *   - `ctrl` is a 64-byte device control block (scrna_nmf_ctrl_t).  When ctrl->done != 0 every
+ *     kernel of the iteration returns immediately, so a loop can be enqueued (or graph-replayed)
+ *     past convergence without host synchronisation.  ctrl may be NULL for one-shot calls.
+ */
+#ifndef SCRNA_B200_H
+#define SCRNA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCRNA_OK 0
+#define SCRNA_ERR_BADARG (-1)
+#define SCRNA_ERR_CUDA (-2)
+#define SCRNA_ERR_UNSUPPORTED (-3)
+
+#define SCRNA_FLAG_NAN 1       /* a factor entry became NaN (nmf_clustering.py:33-38)          */
+#define SCRNA_FLAG_ZERO_DEN 2  /* zero denominator in the target MU step (utils.py:199-200)    */
+
+#define SCRNA_SOLVER_MU 0 /* SP/sklearn/decomposition/_nmf.py:521-723 (Frobenius multiplicative update) */
+#define SCRNA_SOLVER_CD 1 /* SP/sklearn/decomposition/_cdnmf_fast.pyx:8-38 (coordinate descent)         */
+
+#define SCRNA_MAX_K 64
+
+typedef struct scrna_nmf_ctrl {
+  int32_t iter;     /* completed iterations                                   */
+  int32_t done;     /* 1 once the stop rule fired                             */
+  int32_t n_iter;   /* iteration at which it fired (sklearn's n_iter)         */
+  int32_t flags;    /* SCRNA_FLAG_*                                           */
+  double viol_init; /* CD: violation of iteration 1 (_nmf.py:504-505)         */
+  double viol_last; /* CD: violation of the last completed iteration          */
+  double err_last;  /* MU / transfer: last error scalar                       */
+  double reserved[3];
+} scrna_nmf_ctrl_t;
+
+/* ---- library / device ------------------------------------------------------------------ */
+/* Version of the ABI (bumped on any signature change). */
+int scrna_abi_version(void);
+/* Fills sm_count / max dynamic smem per block of the current device. */
+int scrna_device_info(int* sm_count, int* max_smem_per_block, int* cc_major, int* cc_minor);
+
+/* ---- NMF iteration (NmfClustering.apply, nmf_clustering.py:20-42; NmfClustering_initW.apply,
+ *      nmf_clustering.py:59-85; DaNmfClustering.apply :207-223) ------------------------------
+ * One sklearn iteration (_nmf.py:491-502) = gene-factor half step + cell-factor half step, each
+ *   sweep of X (K1 / K3)  ->  reduce partials  ->  [all-reduce across cell shards]  ->  epilogue.
+ */
+
+/* Recommended split counts for the two sweeps on the current device (grid = tiles x splits is
+ * sized to a multiple of SM count x resident CTAs). */
+int scrna_nmf_xht_splits(int g, int64_t ncols, int kp);
+int scrna_nmf_wtx_splits(int g, int64_t ncols, int kp);
+
+/* K1 xht_partial: part[s][i][t] = sum_{j in cell span s} X[i][j] * C32[t][j]   (X . C^T, reduces
+ * over the contiguous axis).  Replaces safe_sparse_dot(X, Ht) in _update_coordinate_descent
+ * (_nmf.py:381) / the numerator X.H^T of _multiplicative_update_w (_nmf.py:537-538).
+ * part: nsplit x g x kp fp32.  variant: 0 = default kernel. */
+int scrna_nmf_xht_partial(const float* X, int64_t ldx, int g, int64_t ncols, const float* C32,
+                          int64_t ldc, int kp, float* part, int nsplit, int variant,
+                          const scrna_nmf_ctrl_t* ctrl, void* stream);
+
+/* K3 wtx_partial: part[s][t][j] = sum_{i in gene span s} G32[i][t] * X[i][j]   (G^T . X, cells own
+ * their output).  Replaces safe_sparse_dot(X.T, W) (_nmf.py:381 via :499-501) / W^T.X of
+ * _multiplicative_update_h (_nmf.py:644) / W.T.dot(trg_data) (utils.py:201).
+ * part: nsplit x kp x ldc fp32. */
+int scrna_nmf_wtx_partial(const float* X, int64_t ldx, int g, int64_t ncols, const float* G32, int kp,
+                          float* part, int64_t ldc, int nsplit, int variant,
+                          const scrna_nmf_ctrl_t* ctrl, void* stream);
+
+/* Sum the K1 partials over the splits in fixed order into fp64: out[i][t] (g x kp). */
+int scrna_nmf_reduce_rows(const float* part, int nsplit, int g, int kp, double* out,
+                          const scrna_nmf_ctrl_t* ctrl, void* stream);
+/* Sum the K3 partials over the splits in fixed order into fp64: out[t][j] (kp x ldc). */
+int scrna_nmf_reduce_cols(const float* part, int nsplit, int kp, int64_t ldc, int64_t ncols,
+                          double* out, const scrna_nmf_ctrl_t* ctrl, void* stream);
+
+/* K4 gram: out[a][b] = sum_r F[r*rs + a*cs] * F[r*rs + b*cs], a,b < k, written as kp x kp fp64
+ * (padding zero).  HHt = Ht^T.Ht / W^T.W of _nmf.py:380,536.  `partials` is scratch of
+ * scrna_nmf_gram_blocks() * kp*kp doubles; the result is summed in fixed block order. */
+int scrna_nmf_gram_blocks(void);
+int scrna_nmf_gram(const double* F, int64_t rs, int64_t cs, int64_t rows, int k, int kp,
+                   double* partials, double* out, const scrna_nmf_ctrl_t* ctrl, void* stream);
+
+/* K2 / K3-epilogue: update one factor in place (fp64 master F64 and fp32 shadow F32 share the
+ * element layout F[r*rs + t*cs], r < rows, t < k).
+ *   num  : fp64 products (rows x kp if cs == 1 i.e. gene factor, else kp x ldc i.e. cell factor),
+ *          same element layout as F;
+ *   gram : kp x kp fp64 Gram of the OTHER factor;
+ *   solver MU: F *= num / (F.gram + l1 + l2*F), zero denominators -> float32 eps
+ *              (_nmf.py:521-626, 629-723);
+ *   solver CD: num -= l1; gram.diag += l2; for t in perm: projected-gradient step
+ *              (_nmf.py:369-396 + _cdnmf_fast.pyx:8-38); perm = perms[(ctrl->iter*perm_stride +
+ *              perm_offset) * kp .. +k) is the pre-drawn RandomState stream;
+ *   viol_part: scrna_nmf_update_blocks(rows) doubles, per-block sums of |projected gradient|.
+ */
+int scrna_nmf_update_blocks(int64_t rows);
+int scrna_nmf_update(int solver, double* F64, float* F32, int64_t rs, int64_t cs, int64_t rows, int k,
+                     int kp, const double* num, const double* gram, double l1, double l2,
+                     const int32_t* perms, int perm_stride, int perm_offset, double* viol_part,
+                     scrna_nmf_ctrl_t* ctrl, void* stream);
+
+/* End of one CD iteration: violation = sum(viol_a[0..na)) + sum(viol_b[0..nb)) in fixed order;
+ * first iteration stores viol_init; done if viol_init == 0 or violation / viol_init <= tol
+ * (_nmf.py:504-516); ++iter.  With tol < 0 only the counter advances (MU). */
+int scrna_nmf_iter_end(scrna_nmf_ctrl_t* ctrl, const double* viol_a, int na, const double* viol_b,
+                       int nb, double tol, int max_iter, void* stream);
+
+/* Zero a control block. */
+int scrna_nmf_ctrl_reset(scrna_nmf_ctrl_t* ctrl, void* stream);
+
+/* fp64 master -> fp32 shadow (same layout, `count` elements). */
+int scrna_cast_f64_f32(const double* src, float* dst, int64_t count, void* stream);
+/* fp64 host-layout matrix (rows x cols, ld_src) -> fp32 (ld_dst >= cols, padding zeroed). */
+int scrna_convert_pad_f64_f32(const double* src, int64_t ld_src, float* dst, int64_t ld_dst,
+                              int64_t rows, int64_t cols, void* stream);
+
+/* ---- residuals (K7): sum_{i,j} |X - G.C|^p over the whole shard, p = 1 (utils.py:202, target
+ * transfer error) or p = 2 (squared Frobenius, _nmf.py:866-879 convergence test of solver='mu').
+ * partials: scrna_residual_blocks(ncols, kp) doubles; out: 1 double (fixed-order sum). */
+int scrna_residual_blocks(int64_t ncols, int kp);
+int scrna_residual(const float* X, int64_t ldx, int g, int64_t ncols, const float* G32, const float* C32,
+                   int64_t ldc, int kp, int power, double* partials, double* out, void* stream);
+
+/* out[0] = scale * sum(v[0..n)) in a fixed order (block partial sums -> one scalar; used for the
+ * sharded part of the CD violation and for the error scalars before their all-reduce). */
+int scrna_sum_f64(const double* v, int n, double* out, double scale, void* stream);
+
+/* ---- target transfer (utils.get_transferred_data_matrix, utils.py:187-230; DaNmfClustering
+ *      .get_mixed_data / .calc_rejection, nmf_clustering.py:147-205, 225-272) ------------------ */
+
+/* K6: one multiplicative step with W fixed: H[t][j] *= WtX[t][j] / sum_q WtW[t][q] * H[q][j]
+ * (utils.py:201 with (W^T W).H in place of W^T.(W.H)); an exactly-zero denominator sets
+ * SCRNA_FLAG_ZERO_DEN in ctrl->flags (utils.py:199-200 raises 'DA target: division by zero.'). */
+int scrna_transfer_mu_step(double* H64, float* H32, const double* WtX, const double* WtW, int k, int kp,
+                           int64_t ncols, int64_t ldc, scrna_nmf_ctrl_t* ctrl, void* stream);
+
+/* labels[j] = argmax_t H64[t][j], ties -> lowest t (np.argmax; utils.py:210, nmf_clustering.py:170). */
+int scrna_argmax_cols(const double* H64, int k, int64_t ncols, int64_t ldc, int32_t* labels, void* stream);
+
+/* K8: mixed = mix * W[:, labels] + (1 - mix) * X  and  new_trg = W[:, labels]  (W.H2 with one-hot
+ * H2; nmf_clustering.py:185,200).  Any of mixed64 / mixed32 / newtrg64 may be NULL.  mixed32 is the
+ * device-resident fp32 copy (leading dimension ld32, padding zeroed) the SC3 stage consumes. */
+int scrna_mix_gather(const float* X, int64_t ldx, int g, int64_t ncols, const double* G64, int kp,
+                     const int32_t* labels, double mix, double* mixed64, int64_t ld64, float* mixed32,
+                     int64_t ld32, double* newtrg64, void* stream);
+
+/* Per-cell rejection statistics in one sweep (nmf_clustering.py:236-271): out is 5 x ldo fp64:
+ * column sums of X, L1 and squared-L2 residuals against W.H, then against W.H2. */
+int scrna_reject_stats(const float* X, int64_t ldx, int g, int64_t ncols, const double* G64, int k, int kp,
+                       const double* H64, int64_t ldc, const int32_t* labels, double* out, int64_t ldo,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCRNA_B200_H */

@@ -1,0 +1,358 @@
+// NMF epilogues for sm_100a: partial reduction, k x k Grams, the multiplicative-update and
+// coordinate-descent factor updates, and the device-side stop rule.
+//
+// These operate on the small rank-k factors (g x k and k x n) in fp64 -- the reference computes
+// everything in float64 (abstract_clustering.py:28) and only the X products are accumulated in
+// fp32 by the sweeps -- and write the fp32 shadow the next sweep reads.
+#include "common.cuh"
+
+namespace scrna {
+
+constexpr int UPD_THREADS = 128;
+
+// ---- fixed-order reduction of the sweep partials ---------------------------------------------
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nsplit, int64_t count,
+                                       int64_t split_stride, double* __restrict__ out,
+                                       const NmfCtrl* __restrict__ ctrl) {
+  if (ctrl_done(ctrl)) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int p = 0; p < nsplit; ++p) s += (double)part[(int64_t)p * split_stride + i];
+    out[i] = s;
+  }
+}
+
+// ---- Gram of a factor: out[a][b] = sum_r F[r*rs + a*cs] * F[r*rs + b*cs] -----------------------
+constexpr int GRAM_TILE = 64;     // rows per smem tile
+constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_BLOCKS = 128;
+
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_partial_kernel(const double* __restrict__ F, int64_t rs, int64_t cs, int64_t rows, int k, int kp,
+                    double* __restrict__ partials, const NmfCtrl* __restrict__ ctrl) {
+  if (ctrl_done(ctrl)) return;
+  extern __shared__ double tile[];  // GRAM_TILE x (k+1)
+  const int kk = k * k;
+  const int ldt = k + 1;
+  // each thread owns outputs o = threadIdx.x, +GRAM_THREADS, ... (k*k <= 4096 -> <= 16 each)
+  double acc[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+
+  for (int64_t r0 = (int64_t)blockIdx.x * GRAM_TILE; r0 < rows; r0 += (int64_t)gridDim.x * GRAM_TILE) {
+    const int nr = (int)min((int64_t)GRAM_TILE, rows - r0);
+    __syncthreads();
+    if (cs == 1) {  // row-major factor: consecutive threads walk along the components
+      for (int i = threadIdx.x; i < nr * k; i += GRAM_THREADS) {
+        const int r = i / k, a = i - r * k;
+        tile[r * ldt + a] = F[(r0 + r) * rs + a];
+      }
+    } else {  // component-major factor (k x ld): consecutive threads walk along the rows
+      for (int i = threadIdx.x; i < nr * k; i += GRAM_THREADS) {
+        const int a = i / nr, r = i - a * nr;
+        tile[r * ldt + a] = F[(r0 + r) * rs + (int64_t)a * cs];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int o = threadIdx.x + q * GRAM_THREADS;
+      if (o < kk) {
+        const int a = o / k, b = o - a * k;
+        double s = acc[q];
+        for (int r = 0; r < nr; ++r) s = fma(tile[r * ldt + a], tile[r * ldt + b], s);
+        acc[q] = s;
+      }
+    }
+  }
+  double* out = partials + (int64_t)blockIdx.x * kp * kp;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int o = threadIdx.x + q * GRAM_THREADS;
+    if (o < kk) {
+      const int a = o / k, b = o - a * k;
+      out[a * kp + b] = acc[q];
+    }
+  }
+}
+
+__global__ void gram_final_kernel(const double* __restrict__ partials, int nblk, int k, int kp,
+                                  double* __restrict__ out, const NmfCtrl* __restrict__ ctrl) {
+  if (ctrl_done(ctrl)) return;
+  for (int o = threadIdx.x; o < kp * kp; o += blockDim.x) {
+    const int a = o / kp, b = o - a * kp;
+    double s = 0.0;
+    if (a < k && b < k)
+      for (int p = 0; p < nblk; ++p) s += partials[(int64_t)p * kp * kp + o];
+    out[o] = s;
+  }
+}
+
+// ---- factor update ---------------------------------------------------------------------------
+// One thread per factor row r (a gene of G, or a cell of C).  The row's k entries live in shared
+// memory as sw[t * UPD_THREADS + tid] so that the CD sweep can index them by the (uniform)
+// permuted component without spilling registers; the k x k Gram is broadcast from shared memory.
+template <int SOLVER>
+__global__ void __launch_bounds__(UPD_THREADS)
+update_kernel(double* __restrict__ F64, float* __restrict__ F32, int64_t rs, int64_t cs, int64_t rows,
+              int k, int kp, const double* __restrict__ num, const double* __restrict__ gram, double l1,
+              double l2, const int32_t* __restrict__ perms, int perm_stride, int perm_offset,
+              double* __restrict__ viol_part, NmfCtrl* __restrict__ ctrl) {
+  if (ctrl_done(ctrl)) return;
+  extern __shared__ double smem[];
+  double* sg = smem;                         // kp*kp Gram
+  double* sw = sg + kp * kp;                 // k * UPD_THREADS factor entries
+  double* sn = sw + (size_t)k * UPD_THREADS; // k * UPD_THREADS numerators
+  __shared__ double scratch[32];
+  __shared__ int sperm[SCRNA_MAX_K];
+  __shared__ int snan;
+
+  const int tid = threadIdx.x;
+  for (int o = tid; o < kp * kp; o += UPD_THREADS) sg[o] = gram[o];
+  if (SOLVER == SCRNA_SOLVER_CD && tid < k) {
+    const int it = ctrl ? ctrl->iter : 0;
+    sperm[tid] = perms ? perms[((int64_t)it * perm_stride + perm_offset) * kp + tid] : tid;
+  }
+  if (tid == 0) snan = 0;
+  __syncthreads();
+
+  const int64_t r = (int64_t)blockIdx.x * UPD_THREADS + tid;
+  const bool live = r < rows;
+  double viol = 0.0;
+  bool nan_seen = false;
+  if (live) {
+    for (int t = 0; t < k; ++t) {
+      const int64_t e = r * rs + (int64_t)t * cs;
+      sw[t * UPD_THREADS + tid] = F64[e];
+      sn[t * UPD_THREADS + tid] = num[e];
+    }
+    if (SOLVER == SCRNA_SOLVER_MU) {
+      // W *= XHt / (W.HHt + l1 + l2*W); the denominator uses the OLD row throughout
+      for (int t = 0; t < k; ++t) {
+        double den = 0.0;
+        for (int q = 0; q < k; ++q) den += sw[q * UPD_THREADS + tid] * sg[q * kp + t];
+        const double w = sw[t * UPD_THREADS + tid];
+        if (l1 > 0.0) den += l1;
+        if (l2 > 0.0) den = den + l2 * w;
+        if (den == 0.0) den = (double)kEpsMU;
+        const double v = w * (sn[t * UPD_THREADS + tid] / den);
+        sn[t * UPD_THREADS + tid] = v;  // numerator no longer needed: reuse as the new value
+      }
+      for (int t = 0; t < k; ++t) {
+        const double v = sn[t * UPD_THREADS + tid];
+        nan_seen |= (v != v);
+        const int64_t e = r * rs + (int64_t)t * cs;
+        F64[e] = v;
+        F32[e] = (float)v;
+      }
+    } else {
+      // _update_cdnmf_fast with HHt.diag += l2 and XHt -= l1 (_nmf.py:383-388)
+      for (int s = 0; s < k; ++s) {
+        const int t = sperm[s];
+        double grad = -(sn[t * UPD_THREADS + tid] - l1);
+        for (int q = 0; q < k; ++q) {
+          double h = sg[t * kp + q];
+          if (q == t) h += l2;
+          grad += h * sw[q * UPD_THREADS + tid];
+        }
+        const double w = sw[t * UPD_THREADS + tid];
+        const double pg = (w == 0.0) ? fmin(0.0, grad) : grad;
+        viol += fabs(pg);
+        const double hess = sg[t * kp + t] + l2;
+        if (hess != 0.0) sw[t * UPD_THREADS + tid] = fmax(w - grad / hess, 0.0);
+      }
+      for (int t = 0; t < k; ++t) {
+        const double v = sw[t * UPD_THREADS + tid];
+        nan_seen |= (v != v);
+        const int64_t e = r * rs + (int64_t)t * cs;
+        F64[e] = v;
+        F32[e] = (float)v;
+      }
+    }
+  }
+  if (nan_seen) snan = 1;
+  const double bsum = block_sum(viol, scratch);  // contains __syncthreads
+  if (tid == 0) {
+    if (viol_part) viol_part[blockIdx.x] = bsum;
+    if (snan && ctrl) atomicOr(&ctrl->flags, SCRNA_FLAG_NAN);
+  }
+}
+
+__global__ void iter_end_kernel(NmfCtrl* ctrl, const double* __restrict__ va, int na,
+                                const double* __restrict__ vb, int nb, double tol, int max_iter) {
+  if (ctrl->done) return;
+  // fixed-order sums, one warp
+  double s = 0.0;
+  const int lane = threadIdx.x;
+  for (int i = lane; i < na; i += 32) s += va[i];
+  double a = warp_sum(s);
+  s = 0.0;
+  for (int i = lane; i < nb; i += 32) s += vb[i];
+  double b = warp_sum(s);
+  if (lane == 0) {
+    const double v = a + b;
+    const int it = ctrl->iter + 1;
+    ctrl->iter = it;
+    if (tol >= 0.0) {
+      ctrl->viol_last = v;
+      if (it == 1) ctrl->viol_init = v;
+      const double vi = ctrl->viol_init;
+      if (vi == 0.0 || v / vi <= tol) {
+        ctrl->done = 1;
+        ctrl->n_iter = it;
+      }
+    }
+    if (!ctrl->done && it >= max_iter) {
+      ctrl->done = 1;
+      ctrl->n_iter = it;
+    }
+  }
+}
+
+__global__ void ctrl_reset_kernel(NmfCtrl* ctrl) {
+  if (threadIdx.x == 0) {
+    ctrl->iter = 0; ctrl->done = 0; ctrl->n_iter = 0; ctrl->flags = 0;
+    ctrl->viol_init = 0.0; ctrl->viol_last = 0.0; ctrl->err_last = 0.0;
+    ctrl->reserved[0] = ctrl->reserved[1] = ctrl->reserved[2] = 0.0;
+  }
+}
+
+__global__ void cast_kernel(const double* __restrict__ src, float* __restrict__ dst, int64_t count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
+
+__global__ void convert_pad_kernel(const double* __restrict__ src, int64_t ld_src, float* __restrict__ dst,
+                                   int64_t ld_dst, int64_t rows, int64_t cols) {
+  const int64_t r = blockIdx.y;
+  if (r >= rows) return;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ld_dst;
+       c += (int64_t)gridDim.x * blockDim.x)
+    dst[r * ld_dst + c] = c < cols ? (float)src[r * ld_src + c] : 0.f;
+}
+
+static int grid_for(int64_t count, int threads) {
+  int64_t b = ceil_div(count, threads);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace scrna
+
+using namespace scrna;
+
+extern "C" int scrna_abi_version(void) { return 1; }
+
+extern "C" int scrna_device_info(int* sm_count, int* max_smem_per_block, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return SCRNA_ERR_CUDA;
+  int v = 0;
+  if (sm_count) { cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); *sm_count = v; }
+  if (max_smem_per_block) { cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); *max_smem_per_block = v; }
+  if (cc_major) { cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev); *cc_major = v; }
+  if (cc_minor) { cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev); *cc_minor = v; }
+  return last_launch_status();
+}
+
+extern "C" int scrna_nmf_reduce_rows(const float* part, int nsplit, int g, int kp, double* out,
+                                     const scrna_nmf_ctrl_t* ctrl, void* stream) {
+  if (!part || !out || nsplit <= 0 || g <= 0 || kp <= 0) return SCRNA_ERR_BADARG;
+  const int64_t count = (int64_t)g * kp;
+  reduce_partials_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(
+      part, nsplit, count, count, out, (const NmfCtrl*)ctrl);
+  return last_launch_status();
+}
+
+extern "C" int scrna_nmf_reduce_cols(const float* part, int nsplit, int kp, int64_t ldc, int64_t ncols,
+                                     double* out, const scrna_nmf_ctrl_t* ctrl, void* stream) {
+  if (!part || !out || nsplit <= 0 || kp <= 0 || ldc <= 0 || ncols > ldc) return SCRNA_ERR_BADARG;
+  const int64_t count = (int64_t)kp * ldc;
+  reduce_partials_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(
+      part, nsplit, count, count, out, (const NmfCtrl*)ctrl);
+  return last_launch_status();
+}
+
+extern "C" int scrna_nmf_gram_blocks(void) { return GRAM_BLOCKS; }
+
+extern "C" int scrna_nmf_gram(const double* F, int64_t rs, int64_t cs, int64_t rows, int k, int kp,
+                              double* partials, double* out, const scrna_nmf_ctrl_t* ctrl, void* stream) {
+  if (!F || !partials || !out || rows <= 0 || k <= 0 || k > kp || kp > SCRNA_MAX_K) return SCRNA_ERR_BADARG;
+  int nblk = (int)ceil_div(rows, GRAM_TILE);
+  if (nblk > GRAM_BLOCKS) nblk = GRAM_BLOCKS;
+  const size_t smem = (size_t)GRAM_TILE * (k + 1) * sizeof(double);
+  cudaStream_t st = (cudaStream_t)stream;
+  gram_partial_kernel<<<nblk, GRAM_THREADS, smem, st>>>(F, rs, cs, rows, k, kp, partials, (const NmfCtrl*)ctrl);
+  gram_final_kernel<<<1, 256, 0, st>>>(partials, nblk, k, kp, out, (const NmfCtrl*)ctrl);
+  return last_launch_status();
+}
+
+extern "C" int scrna_nmf_update_blocks(int64_t rows) { return (int)ceil_div(rows, UPD_THREADS); }
+
+extern "C" int scrna_nmf_update(int solver, double* F64, float* F32, int64_t rs, int64_t cs, int64_t rows,
+                                int k, int kp, const double* num, const double* gram, double l1, double l2,
+                                const int32_t* perms, int perm_stride, int perm_offset, double* viol_part,
+                                scrna_nmf_ctrl_t* ctrl, void* stream) {
+  if (!F64 || !F32 || !num || !gram || rows <= 0 || k <= 0 || k > kp || kp > SCRNA_MAX_K)
+    return SCRNA_ERR_BADARG;
+  const size_t smem = ((size_t)kp * kp + 2 * (size_t)k * UPD_THREADS) * sizeof(double);
+  const int nblk = (int)ceil_div(rows, UPD_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(update_kernel<SCRNA_SOLVER_MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(update_kernel<SCRNA_SOLVER_CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  if (solver == SCRNA_SOLVER_MU)
+    update_kernel<SCRNA_SOLVER_MU><<<nblk, UPD_THREADS, smem, st>>>(F64, F32, rs, cs, rows, k, kp, num, gram, l1, l2,
+                                                                  perms, perm_stride, perm_offset, viol_part,
+                                                                  (NmfCtrl*)ctrl);
+  else if (solver == SCRNA_SOLVER_CD)
+    update_kernel<SCRNA_SOLVER_CD><<<nblk, UPD_THREADS, smem, st>>>(F64, F32, rs, cs, rows, k, kp, num, gram, l1, l2,
+                                                                  perms, perm_stride, perm_offset, viol_part,
+                                                                  (NmfCtrl*)ctrl);
+  else
+    return SCRNA_ERR_BADARG;
+  return last_launch_status();
+}
+
+extern "C" int scrna_nmf_iter_end(scrna_nmf_ctrl_t* ctrl, const double* viol_a, int na, const double* viol_b,
+                                  int nb, double tol, int max_iter, void* stream) {
+  if (!ctrl) return SCRNA_ERR_BADARG;
+  iter_end_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((NmfCtrl*)ctrl, viol_a, viol_a ? na : 0, viol_b,
+                                                      viol_b ? nb : 0, tol, max_iter);
+  return last_launch_status();
+}
+
+extern "C" int scrna_nmf_ctrl_reset(scrna_nmf_ctrl_t* ctrl, void* stream) {
+  if (!ctrl) return SCRNA_ERR_BADARG;
+  ctrl_reset_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((NmfCtrl*)ctrl);
+  return last_launch_status();
+}
+
+extern "C" int scrna_cast_f64_f32(const double* src, float* dst, int64_t count, void* stream) {
+  if (!src || !dst || count < 0) return SCRNA_ERR_BADARG;
+  if (count == 0) return SCRNA_OK;
+  cast_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, count);
+  return last_launch_status();
+}
+
+extern "C" int scrna_convert_pad_f64_f32(const double* src, int64_t ld_src, float* dst, int64_t ld_dst,
+                                         int64_t rows, int64_t cols, void* stream) {
+  if (!src || !dst || rows <= 0 || cols <= 0 || cols > ld_src || cols > ld_dst || rows > 65535 * 64LL)
+    return SCRNA_ERR_BADARG;
+  // blockIdx.y is limited to 65535: process row bands
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    int bx = (int)ceil_div(ld_dst, 256);
+    if (bx > 64) bx = 64;
+    dim3 grid((unsigned)bx, (unsigned)nr);
+    convert_pad_kernel<<<grid, 256, 0, st>>>(src + r0 * ld_src, ld_src, dst + r0 * ld_dst, ld_dst, nr, cols);
+  }
+  return last_launch_status();
+}

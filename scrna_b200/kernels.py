@@ -1,0 +1,105 @@
+"""Typed wrappers over the C ABI (include/scrna_b200.h) taking torch CUDA tensors.
+
+`CudaKernels` is the ONLY compute provider of the package.  The solvers talk to it through this
+small method set so that the host-side logic (sharding, all-reduce packing, stop rules) can be
+exercised in tests with a stand-in provider; the product never constructs anything else.
+"""
+from . import _lib
+
+
+class CudaKernels:
+    name = "cuda"
+
+    def __init__(self):
+        self.torch = _lib.require_cuda()
+        _lib.load()
+        self.launches = 0  # number of C-ABI kernel-launching calls issued (bench.py: gpu_launches)
+
+    def _s(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def _call(self, name, *args):
+        self.launches += 1
+        return _lib.call(name, *args)
+
+    # ---- sizing -----------------------------------------------------------------------------
+    def xht_splits(self, g, ncols, kp):
+        return _lib.call("scrna_nmf_xht_splits", g, ncols, kp)
+
+    def wtx_splits(self, g, ncols, kp):
+        return _lib.call("scrna_nmf_wtx_splits", g, ncols, kp)
+
+    def gram_blocks(self):
+        return _lib.call("scrna_nmf_gram_blocks")
+
+    def update_blocks(self, rows):
+        return _lib.call("scrna_nmf_update_blocks", rows)
+
+    def residual_blocks(self, ncols, kp):
+        return _lib.call("scrna_residual_blocks", ncols, kp)
+
+    # ---- NMF iteration ------------------------------------------------------------------------
+    def xht_partial(self, X, ldx, g, ncols, C32, ldc, kp, part, nsplit, ctrl, variant=0):
+        self._call("scrna_nmf_xht_partial", X, ldx, g, ncols, C32, ldc, kp, part, nsplit, variant, ctrl, self._s())
+
+    def wtx_partial(self, X, ldx, g, ncols, G32, kp, part, ldc, nsplit, ctrl, variant=0):
+        self._call("scrna_nmf_wtx_partial", X, ldx, g, ncols, G32, kp, part, ldc, nsplit, variant, ctrl, self._s())
+
+    def reduce_rows(self, part, nsplit, g, kp, out, ctrl):
+        self._call("scrna_nmf_reduce_rows", part, nsplit, g, kp, out, ctrl, self._s())
+
+    def reduce_cols(self, part, nsplit, kp, ldc, ncols, out, ctrl):
+        self._call("scrna_nmf_reduce_cols", part, nsplit, kp, ldc, ncols, out, ctrl, self._s())
+
+    def gram(self, F64, rs, cs, rows, k, kp, partials, out, ctrl):
+        self.launches += 1  # two kernels per call
+        self._call("scrna_nmf_gram", F64, rs, cs, rows, k, kp, partials, out, ctrl, self._s())
+
+    def update(self, solver, F64, F32, rs, cs, rows, k, kp, num, gram, l1, l2, perms, perm_stride, perm_offset,
+               viol_part, ctrl):
+        self._call("scrna_nmf_update", solver, F64, F32, rs, cs, rows, k, kp, num, gram, float(l1), float(l2),
+                   perms, perm_stride, perm_offset, viol_part, ctrl, self._s())
+
+    def iter_end(self, ctrl, viol_a, na, viol_b, nb, tol, max_iter):
+        self._call("scrna_nmf_iter_end", ctrl, viol_a, na, viol_b, nb, float(tol), int(max_iter), self._s())
+
+    def ctrl_reset(self, ctrl):
+        self._call("scrna_nmf_ctrl_reset", ctrl, self._s())
+
+    def cast_f64_f32(self, src, dst, count):
+        self._call("scrna_cast_f64_f32", src, dst, count, self._s())
+
+    def convert_pad(self, src, ld_src, dst, ld_dst, rows, cols):
+        self._call("scrna_convert_pad_f64_f32", src, ld_src, dst, ld_dst, rows, cols, self._s())
+
+    def residual(self, X, ldx, g, ncols, G32, C32, ldc, kp, power, partials, out):
+        self.launches += 1
+        self._call("scrna_residual", X, ldx, g, ncols, G32, C32, ldc, kp, power, partials, out, self._s())
+
+    def sum_f64(self, v, n, out, scale=1.0):
+        self._call("scrna_sum_f64", v, n, out, float(scale), self._s())
+
+    # ---- target transfer ------------------------------------------------------------------------
+    def transfer_mu_step(self, H64, H32, WtX, WtW, k, kp, ncols, ldc, ctrl):
+        self._call("scrna_transfer_mu_step", H64, H32, WtX, WtW, k, kp, ncols, ldc, ctrl, self._s())
+
+    def argmax_cols(self, H64, k, ncols, ldc, labels):
+        self._call("scrna_argmax_cols", H64, k, ncols, ldc, labels, self._s())
+
+    def mix_gather(self, X, ldx, g, ncols, G64, kp, labels, mix, mixed64, ld64, mixed32, ld32, newtrg64):
+        self._call("scrna_mix_gather", X, ldx, g, ncols, G64, kp, labels, float(mix), mixed64, ld64, mixed32, ld32,
+                   newtrg64, self._s())
+
+    def reject_stats(self, X, ldx, g, ncols, G64, k, kp, H64, ldc, labels, out, ldo):
+        self._call("scrna_reject_stats", X, ldx, g, ncols, G64, k, kp, H64, ldc, labels, out, ldo, self._s())
+
+
+_default = None
+
+
+def default_kernels():
+    """The process-wide CUDA provider (raises without a GPU or without the built library)."""
+    global _default
+    if _default is None:
+        _default = CudaKernels()
+    return _default

@@ -1,0 +1,327 @@
+"""Host loop of the B200 NMF solver: device-resident X shard, alternating factor updates.
+
+One iteration (sklearn `_fit_coordinate_descent` loop body, SP/sklearn/decomposition/_nmf.py:491-502,
+or `_fit_multiplicative_update`, _nmf.py:826-864) is, for the gene factor G (g x k) and the cell
+factor C (k x n):
+
+    K1  xht_partial(X, C32)  -> reduce_rows -> R.xht (g x kp fp64)         one sweep of X
+    K4  gram(C64)            -> R.cct (kp x kp fp64)
+        [all-reduce R over the cell shards: the ONLY per-iteration collective]
+    K2  update(G | R.xht, R.cct)            (MU ratio or CD sweep; fp64; writes the fp32 shadow)
+    K4  gram(G64)            -> gtg
+    K3  wtx_partial(X, G32)  -> reduce_cols -> nb (kp x ldc fp64)          second sweep of X
+        update(C | nb, gtg)                 (cells are local to the shard: no communication)
+        iter_end                            (device-side stop rule, _nmf.py:504-516)
+
+`first='C'` runs the cell half-step first (NmfClustering_initW factorises X^T, scRNA/nmf_clustering.py
+:71-72, so sklearn's W is our C^T and is updated first).  The permutation stream of the CD solver is
+pre-drawn on the host from RandomState(seed) in sklearn's consumption order.
+
+Nothing here computes on the CPU: every array op is a C-ABI kernel; the host only sequences them,
+polls the 64-byte control block and (MU) applies the every-10-iterations stop rule to a scalar.
+"""
+import math
+
+import numpy as np
+
+from . import _lib
+
+
+def round_up(a, m):
+    return ((int(a) + m - 1) // m) * m
+
+
+def pad_k(k):
+    if k < 1 or k > _lib.MAX_K:
+        raise ValueError("number of components must be in [1, %d], got %d" % (_lib.MAX_K, k))
+    kp = round_up(k, 4)
+    if kp > 32:
+        kp = round_up(k, 8)
+    return kp
+
+
+def shard_bounds(n_total, world, rank):
+    """Contiguous, balanced split of the cell axis: first `n_total % world` shards get
+    one extra cell."""
+    base, extra = divmod(int(n_total), int(world))
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+class DeviceMatrix:
+    """X shard: genes x cells, row-major fp32 on the device, leading dimension padded to 32 cells
+    (128 B) and zero-filled beyond the real cells."""
+
+    def __init__(self, data, n):
+        self.data = data
+        self.g = int(data.shape[0])
+        self.ldx = int(data.shape[1])
+        self.n = int(n)
+        self.ncols = round_up(self.n, 4)
+        assert self.ldx % 4 == 0 and self.ncols <= self.ldx
+
+    @classmethod
+    def from_host(cls, arr, kernels, device=None, band_bytes=256 << 20):
+        """Upload a host genes x cells array (any float dtype) in row bands; fp64 bands are narrowed
+        on the device (scrna_convert_pad_f64_f32)."""
+        torch = kernels.torch
+        arr = np.asarray(arr)
+        if arr.ndim != 2:
+            raise ValueError("expected a genes x cells matrix")
+        g, n = arr.shape
+        ldx = round_up(max(n, 1), 32)
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        out = torch.empty((g, ldx), dtype=torch.float32, device=dev)
+        if arr.dtype != np.float64:
+            arr = np.ascontiguousarray(arr, dtype=np.float64) if arr.dtype != np.float32 else arr
+        if arr.dtype == np.float32:
+            out.zero_()
+            out[:, :n].copy_(torch.from_numpy(np.ascontiguousarray(arr)), non_blocking=False)
+            return cls(out, n)
+        rows_per_band = max(1, int(band_bytes // max(1, n * 8)))
+        for r0 in range(0, g, rows_per_band):
+            r1 = min(g, r0 + rows_per_band)
+            band = torch.from_numpy(np.ascontiguousarray(arr[r0:r1])).to(dev)
+            kernels.convert_pad(band, n, out[r0:r1], ldx, r1 - r0, n)
+        torch.cuda.current_stream().synchronize()
+        return cls(out, n)
+
+    @classmethod
+    def from_device(cls, t32, n=None):
+        assert t32.dtype == t32.new_empty(0, dtype=t32.dtype).dtype and t32.dim() == 2
+        return cls(t32, t32.shape[1] if n is None else n)
+
+
+class TorchDistComm:
+    """All-reduce plumbing over torch.distributed (NCCL on the GPUs; gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def all_reduce(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+class NmfResult:
+    def __init__(self, G, C, n_iter, flags, violations=None, errors=None):
+        self.G = G            # g x k  float64 (replicated)
+        self.C = C            # k x n_local float64 (this shard's cells)
+        self.n_iter = n_iter
+        self.flags = flags
+        self.violation_init, self.violation_last = violations if violations else (None, None)
+        self.errors = errors
+
+
+class NmfSolver:
+    def __init__(self, X, k, kernels=None, comm=None):
+        if kernels is None:
+            from .kernels import default_kernels
+            kernels = default_kernels()
+        self.kn = kernels
+        self.torch = kernels.torch
+        self.X = X
+        self.k = int(k)
+        self.kp = pad_k(self.k)
+        self.comm = comm if (comm is not None and comm.world > 1) else None
+        t = self.torch
+        dev = X.data.device
+        g, kp, ldc = X.g, self.kp, X.ldx
+        self.ldc = ldc
+        f64, f32 = t.float64, t.float32
+        self.G64 = t.zeros((g, kp), dtype=f64, device=dev)
+        self.G32 = t.zeros((g, kp), dtype=f32, device=dev)
+        self.C64 = t.zeros((kp, ldc), dtype=f64, device=dev)
+        self.C32 = t.zeros((kp, ldc), dtype=f32, device=dev)
+        self.SA = kernels.xht_splits(g, X.ncols, kp)
+        self.SB = kernels.wtx_splits(g, X.ncols, kp)
+        self.PA = t.empty((self.SA, g, kp), dtype=f32, device=dev)
+        self.PB = t.empty((self.SB, kp, ldc), dtype=f32, device=dev)
+        # all-reduce payload: [ X.C^T (g*kp) | C.C^T (kp*kp) | 4 scalars ]
+        self.R = t.zeros(g * kp + kp * kp + 4, dtype=f64, device=dev)
+        self.R_xht = self.R[: g * kp]
+        self.R_cct = self.R[g * kp: g * kp + kp * kp]
+        self.R_scal = self.R[g * kp + kp * kp:]
+        self.NB = t.zeros((kp, ldc), dtype=f64, device=dev)
+        self.gtg = t.zeros(kp * kp, dtype=f64, device=dev)
+        self.gram_part = t.zeros(kernels.gram_blocks() * kp * kp, dtype=f64, device=dev)
+        self.nblkG = kernels.update_blocks(g)
+        self.nblkC = kernels.update_blocks(max(X.n, 1))
+        self.violG = t.zeros(self.nblkG, dtype=f64, device=dev)
+        self.violC = t.zeros(self.nblkC, dtype=f64, device=dev)
+        self.ctrl = t.zeros(16, dtype=t.int32, device=dev)
+        self.res_part = t.zeros(max(1, kernels.residual_blocks(X.ncols, kp)), dtype=f64, device=dev)
+        self.res_out = t.zeros(1, dtype=f64, device=dev)
+        self.perms = None
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def _load_factors(self, G0, C0):
+        t = self.torch
+        X, k = self.X, self.k
+        G0 = np.ascontiguousarray(G0, dtype=np.float64)
+        C0 = np.ascontiguousarray(C0, dtype=np.float64)
+        if G0.shape != (X.g, k) or C0.shape != (k, X.n):
+            raise ValueError("init shapes %s / %s do not match X %dx%d, k=%d" % (G0.shape, C0.shape, X.g, X.n, k))
+        dev = X.data.device
+        self.G64.zero_()
+        self.C64.zero_()
+        self.G64[:, :k].copy_(t.from_numpy(G0).to(dev))
+        self.C64[:k, : X.n].copy_(t.from_numpy(C0).to(dev))
+        self.kn.cast_f64_f32(self.G64, self.G32, self.G64.numel())
+        self.kn.cast_f64_f32(self.C64, self.C32, self.C64.numel())
+
+    def read_ctrl(self):
+        raw = self.ctrl.cpu().numpy()
+        ints = raw[:4]
+        dbl = raw[4:].view(np.float64)
+        return dict(iter=int(ints[0]), done=int(ints[1]), n_iter=int(ints[2]), flags=int(ints[3]),
+                    viol_init=float(dbl[0]), viol_last=float(dbl[1]), err_last=float(dbl[2]))
+
+    def factors_to_host(self):
+        X, k = self.X, self.k
+        G = self.G64[:, :k].cpu().numpy().copy()
+        C = self.C64[:k, : X.n].cpu().numpy().copy()
+        return G, C
+
+    # ---- the two half steps -------------------------------------------------------------------
+    def _products_for_G(self, ctrl):
+        """R.xht = X.C^T (this shard), R.cct = C.C^T (this shard), then the all-reduce."""
+        kn, X = self.kn, self.X
+        kn.xht_partial(X.data, X.ldx, X.g, X.ncols, self.C32, self.ldc, self.kp, self.PA, self.SA, ctrl)
+        kn.reduce_rows(self.PA, self.SA, X.g, self.kp, self.R_xht, ctrl)
+        kn.gram(self.C64, 1, self.ldc, max(X.n, 1), self.k, self.kp, self.gram_part, self.R_cct, ctrl)
+
+    def _allreduce_R(self):
+        if self.comm is not None:
+            self.comm.all_reduce(self.R)
+
+    def _update_G(self, solver, l1, l2, stride, offset, ctrl):
+        self.kn.update(solver, self.G64, self.G32, self.kp, 1, self.X.g, self.k, self.kp, self.R_xht, self.R_cct,
+                       l1, l2, self.perms, stride, offset, self.violG, ctrl)
+
+    def _half_C(self, solver, l1, l2, stride, offset, ctrl):
+        kn, X = self.kn, self.X
+        kn.gram(self.G64, self.kp, 1, X.g, self.k, self.kp, self.gram_part, self.gtg, ctrl)
+        kn.wtx_partial(X.data, X.ldx, X.g, X.ncols, self.G32, self.kp, self.PB, self.ldc, self.SB, ctrl)
+        kn.reduce_cols(self.PB, self.SB, self.kp, self.ldc, X.ncols, self.NB, ctrl)
+        kn.update(solver, self.C64, self.C32, 1, self.ldc, max(X.n, 1), self.k, self.kp, self.NB, self.gtg,
+                  l1, l2, self.perms, stride, offset, self.violC, ctrl)
+
+    def frobenius_error(self):
+        """||X - G.C||_F over all shards (sklearn _beta_divergence(..., square_root=True))."""
+        X = self.X
+        self.kn.residual(X.data, X.ldx, X.g, X.ncols, self.G32, self.C32, self.ldc, self.kp, 2, self.res_part,
+                         self.res_out)
+        if self.comm is not None:
+            self.comm.all_reduce(self.res_out)
+        return math.sqrt(max(float(self.res_out.cpu()[0]), 0.0))
+
+    # ---- public -------------------------------------------------------------------------------
+    def fit(self, G0, C0, solver="cd", l1_G=0.0, l2_G=0.0, l1_C=0.0, l2_C=0.0, tol=1e-4, max_iter=200,
+            update_G=True, update_C=True, first="G", seed=0, shuffle=True, perms=None, poll=4,
+            to_host=True):
+        """Run the alternating updates from (G0, C0).  Returns NmfResult.
+
+        solver 'cd' reproduces sklearn's coordinate descent (stop: violation/violation_init <= tol),
+        solver 'mu' sklearn's multiplicative update (stop: every 10 iterations,
+        (previous_error - error)/error_at_init < tol; tol=0 runs exactly max_iter iterations)."""
+        if solver not in ("cd", "mu"):
+            raise ValueError("solver must be 'cd' or 'mu'")
+        if first not in ("G", "C"):
+            raise ValueError("first must be 'G' or 'C'")
+        if not (update_G or update_C):
+            raise ValueError("nothing to update")
+        t, kn = self.torch, self.kn
+        code = _lib.SOLVER_CD if solver == "cd" else _lib.SOLVER_MU
+        max_iter = int(max_iter)
+        self._load_factors(G0, C0)
+        ctrl = self.ctrl
+        kn.ctrl_reset(ctrl)
+
+        draws = int(update_G) + int(update_C)
+        if solver == "cd":
+            if perms is None:
+                rng = np.random.RandomState(seed)
+                host = np.zeros((max(1, max_iter) * draws, self.kp), dtype=np.int32)
+                for i in range(host.shape[0]):
+                    host[i, : self.k] = rng.permutation(self.k) if shuffle else np.arange(self.k)
+            else:
+                p = np.asarray(perms, dtype=np.int32)
+                host = np.zeros((p.shape[0], self.kp), dtype=np.int32)
+                host[:, : self.k] = p
+                if host.shape[0] < max_iter * draws:
+                    raise ValueError("not enough pre-drawn permutations")
+            self.perms = t.from_numpy(host).to(self.X.data.device)
+        else:
+            self.perms = None
+        offG = 0 if (first == "G" or not update_C) else 1
+        offC = 0 if (first == "C" or not update_G) else 1
+        cd_tol = float(tol) if solver == "cd" else -1.0
+
+        # a fixed factor makes its products constant: compute them once
+        if not update_C:
+            self._products_for_G(None)
+            self._allreduce_R()
+        if not update_G:
+            kn.gram(self.G64, self.kp, 1, self.X.g, self.k, self.kp, self.gram_part, self.gtg, None)
+
+        errors = None
+        error_at_init = previous_error = None
+        if solver == "mu" and tol > 0:
+            error_at_init = previous_error = self.frobenius_error()
+            errors = [(0, error_at_init)]
+
+        def one_iteration():
+            if first == "G":
+                if update_G:
+                    if update_C:
+                        self._products_for_G(ctrl)
+                        self._allreduce_R()
+                    self._update_G(code, l1_G, l2_G, draws, offG, ctrl)
+                if update_C:
+                    self._half_C(code, l1_C, l2_C, draws, offC, ctrl)
+                    if self.comm is not None and solver == "cd":
+                        kn.sum_f64(self.violC, self.nblkC, self.R_scal[0:1])
+                        self.comm.all_reduce(self.R_scal[0:1])
+            else:
+                if update_C:
+                    self._half_C(code, l1_C, l2_C, draws, offC, ctrl)
+                if update_G:
+                    if update_C:
+                        self._products_for_G(ctrl)
+                        if self.comm is not None and solver == "cd":
+                            kn.sum_f64(self.violC, self.nblkC, self.R_scal[0:1])
+                        self._allreduce_R()
+                    self._update_G(code, l1_G, l2_G, draws, offG, ctrl)
+            va, na = (self.violG, self.nblkG) if update_G else (None, 0)
+            if update_C:
+                vb, nb = (self.R_scal, 1) if self.comm is not None else (self.violC, self.nblkC)
+            else:
+                vb, nb = None, 0
+            kn.iter_end(ctrl, va, na, vb, nb, cd_tol, max_iter)
+
+        n_done = 0
+        state = None
+        while n_done < max_iter:
+            one_iteration()
+            n_done += 1
+            if solver == "mu":
+                if tol > 0 and n_done % 10 == 0:
+                    error = self.frobenius_error()
+                    errors.append((n_done, error))
+                    if (previous_error - error) / error_at_init < tol:
+                        break
+                    previous_error = error
+            elif n_done % poll == 0 or n_done == max_iter:
+                state = self.read_ctrl()
+                if state["done"]:
+                    break
+        state = self.read_ctrl()
+        n_iter = state["n_iter"] if (solver == "cd" and state["done"]) else n_done
+        res = NmfResult(None, None, n_iter, state["flags"], (state["viol_init"], state["viol_last"]), errors)
+        if to_host:
+            res.G, res.C = self.factors_to_host()
+        return res

@@ -1,0 +1,205 @@
+"""Parity of the CUDA NMF path (through the C ABI) against the oracle and the reference goldens.
+
+Tolerances are BASELINE.json's: relative Frobenius reconstruction error 1e-4, per-factor relative
+error 1e-3, identical cluster labels.  The sweeps accumulate in fp32, so kernel-level products are
+compared at 2e-5 relative to the fp64 product.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_fro
+from oracle import nmf_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+CLI = dict(alpha=10., l1=0.75, max_iter=4000, rel_err=1e-3)
+TOL_FACTOR = 1e-3
+TOL_RECON = 1e-4
+
+
+def _recon_err(X, W, H):
+    return np.linalg.norm(X - W @ H) / np.linalg.norm(X)
+
+
+def _solver(kernels, X, k):
+    from scrna_b200.nmf_solver import DeviceMatrix, NmfSolver
+    return NmfSolver(DeviceMatrix.from_host(X, kernels), k, kernels=kernels)
+
+
+@pytest.mark.parametrize("g,n,k", [(1000, 1000, 8), (333, 517, 7), (64, 4100, 5), (2500, 130, 16),
+                                   (129, 257, 33), (40, 36, 3), (700, 900, 50), (5, 7, 2)])
+def test_sweeps_match_fp64_products(kernels, g, n, k):
+    torch = kernels.torch
+    rng = np.random.RandomState(g + n + k)
+    X = rng.poisson(2.0, size=(g, n)).astype(np.float64)
+    G = np.abs(rng.randn(g, k))
+    C = np.abs(rng.randn(k, n))
+    slv = _solver(kernels, X, k)
+    slv._load_factors(G, C)
+    slv._products_for_G(None)
+    torch.cuda.synchronize()
+    xht = slv.R_xht.view(g, slv.kp)[:, :k].cpu().numpy()
+    cct = slv.R_cct.view(slv.kp, slv.kp)[:k, :k].cpu().numpy()
+    assert rel_fro(xht, X @ C.T) < 2e-5
+    assert rel_fro(cct, C @ C.T) < 1e-12
+    assert np.all(slv.R_xht.view(g, slv.kp)[:, k:].cpu().numpy() == 0)
+    kernels.gram(slv.G64, slv.kp, 1, g, k, slv.kp, slv.gram_part, slv.gtg, None)
+    kernels.wtx_partial(slv.X.data, slv.X.ldx, g, slv.X.ncols, slv.G32, slv.kp, slv.PB, slv.ldc, slv.SB, None)
+    kernels.reduce_cols(slv.PB, slv.SB, slv.kp, slv.ldc, slv.X.ncols, slv.NB, None)
+    torch.cuda.synchronize()
+    wtx = slv.NB[:k, :n].cpu().numpy()
+    gtg = slv.gtg.view(slv.kp, slv.kp)[:k, :k].cpu().numpy()
+    assert rel_fro(wtx, G.T @ X) < 2e-5
+    assert rel_fro(gtg, G.T @ G) < 1e-12
+    # residuals
+    kernels.residual(slv.X.data, slv.X.ldx, g, slv.X.ncols, slv.G32, slv.C32, slv.ldc, slv.kp, 1, slv.res_part,
+                     slv.res_out)
+    l1 = float(slv.res_out.cpu()[0])
+    assert abs(l1 - np.abs(X - G @ C).sum()) / np.abs(X - G @ C).sum() < 2e-5
+    assert abs(slv.frobenius_error() - np.linalg.norm(X - G @ C)) / np.linalg.norm(X - G @ C) < 2e-5
+
+
+@pytest.mark.parametrize("solver", ["cd", "mu"])
+def test_single_update_matches_oracle(kernels, solver):
+    """One half step with exact fp64 inputs: the epilogue alone, compared at fp64 rounding level."""
+    import scrna_b200._lib as L
+    torch = kernels.torch
+    rng = np.random.RandomState(11)
+    rows, k, kp = 777, 7, 8
+    W = np.abs(rng.randn(rows, k))
+    W[rng.rand(rows, k) < 0.25] = 0.0
+    A = np.abs(rng.randn(50, k))
+    HHt = A.T @ A
+    XHt = np.abs(rng.randn(rows, k)) * 30
+    perm = rng.permutation(k).astype(np.int32)
+    l1, l2 = 7.5, 2.5
+    dev = torch.device("cuda")
+    for layout in ("rows", "cols"):
+        if layout == "rows":
+            rs, cs, ld = kp, 1, kp
+            F = np.zeros((rows, kp)); F[:, :k] = W
+            N = np.zeros((rows, kp)); N[:, :k] = XHt
+        else:
+            ld = 800
+            rs, cs = 1, ld
+            F = np.zeros((kp, ld)); F[:k, :rows] = W.T
+            N = np.zeros((kp, ld)); N[:k, :rows] = XHt.T
+        F64 = torch.from_numpy(F).to(dev)
+        F32 = torch.zeros_like(F64, dtype=torch.float32)
+        num = torch.from_numpy(N).to(dev)
+        Gm = np.zeros((kp, kp)); Gm[:k, :k] = HHt
+        gram = torch.from_numpy(Gm).to(dev)
+        pp = np.zeros((1, kp), dtype=np.int32); pp[0, :k] = perm
+        perms = torch.from_numpy(pp).to(dev)
+        nblk = kernels.update_blocks(rows)
+        viol = torch.zeros(nblk, dtype=torch.float64, device=dev)
+        ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
+        code = L.SOLVER_CD if solver == "cd" else L.SOLVER_MU
+        kernels.update(code, F64, F32, rs, cs, rows, k, kp, num, gram, l1, l2, perms, 1, 0, viol, ctrl)
+        torch.cuda.synchronize()
+        out = F64.cpu().numpy()
+        got = out[:, :k] if layout == "rows" else out[:k, :rows].T
+        Wref = W.copy()
+        if solver == "cd":
+            H2 = HHt.copy(); H2.flat[:: k + 1] += l2
+            v = no.cd_sweep(Wref, H2, XHt - l1, perm)
+            assert abs(float(viol.sum().cpu()) - v) <= 1e-11 * v
+            np.testing.assert_array_equal(got == 0, Wref == 0)
+        else:
+            den = Wref @ HHt + l1 + l2 * Wref
+            den[den == 0] = no.EPSILON
+            Wref = Wref * (XHt / den)
+        np.testing.assert_allclose(got, Wref, rtol=1e-12, atol=1e-300)
+        shadow = F32.cpu().numpy()
+        shadow = shadow[:, :k] if layout == "rows" else shadow[:k, :rows].T
+        np.testing.assert_array_equal(shadow, Wref.astype(np.float32).astype(np.float32) if False else got.astype(np.float32))
+
+
+def test_nmf_clustering_default_data_vs_reference_golden(kernels, default_sim, golden):
+    from scrna_b200 import NmfClustering
+    g = golden("nmf_source")
+    nmf = NmfClustering(default_sim["src"], default_sim["gene_ids"], 8, default_sim["src_labels"])
+    nmf.apply(k=8, **CLI)
+    X = default_sim["src"]
+    assert nmf.n_iter == int(g["nmf_n_iter"])
+    assert rel_fro(nmf.dictionary, g["nmf_W"]) < TOL_FACTOR
+    assert rel_fro(nmf.data_matrix, g["nmf_H"]) < TOL_FACTOR
+    e_ref = _recon_err(X, g["nmf_W"], g["nmf_H"])
+    e_gpu = _recon_err(X, nmf.dictionary, nmf.data_matrix)
+    assert abs(e_gpu - e_ref) / e_ref < TOL_RECON
+    np.testing.assert_array_equal(nmf.cluster_labels, g["nmf_labels"])
+
+
+def test_initw_default_data_vs_reference_golden(kernels, default_sim, golden):
+    from scrna_b200 import NmfClustering_initW
+    g = golden("nmf_source")
+    nmf = NmfClustering_initW(default_sim["src"], default_sim["gene_ids"], 7, default_sim["src_labels"])
+    nmf.apply(k=7, **CLI)
+    assert nmf.n_iter == (2, 163)
+    assert rel_fro(nmf.dictionary, g["initw_dictionary"]) < TOL_FACTOR
+    assert rel_fro(nmf.data_matrix, g["initw_data_matrix"]) < TOL_FACTOR
+    np.testing.assert_array_equal(nmf.cluster_labels, g["initw_labels"])
+
+
+def test_mu_solver_vs_sklearn_golden(kernels, default_sim, golden):
+    g = golden("nmf_source")
+    slv = _solver(kernels, default_sim["src"], 8)
+    res = slv.fit(g["W0"], g["H0"], solver="mu", l1_G=7.5, l2_G=2.5, l1_C=7.5, l2_C=2.5, tol=1e-4, max_iter=200)
+    assert res.n_iter == int(g["mu_n_iter"])
+    assert rel_fro(res.G, g["mu_W"]) < TOL_FACTOR
+    assert rel_fro(res.C, g["mu_H"]) < TOL_FACTOR
+    X = default_sim["src"]
+    e_ref = _recon_err(X, g["mu_W"], g["mu_H"])
+    assert abs(_recon_err(X, res.G, res.C) - e_ref) / e_ref < TOL_RECON
+
+
+@pytest.mark.parametrize("g,n,k,solver", [(300, 220, 5, "cd"), (257, 1030, 12, "cd"), (300, 220, 5, "mu"),
+                                          (120, 333, 20, "mu"), (90, 75, 3, "cd")])
+def test_fit_vs_oracle_seeded(kernels, g, n, k, solver):
+    rng = np.random.RandomState(g * 7 + n)
+    mu = rng.gamma(2.0, 1.0, size=(g, 1)) * (1 + (rng.rand(g, 6) < 0.2) @ (rng.rand(6, n) < 0.3) * 3.0)
+    X = rng.poisson(mu).astype(np.float64)
+    W0, H0 = no.nndsvdar_init(X, k)
+    l1, l2 = 0.75, 0.25
+    slv = _solver(kernels, X, k)
+    if solver == "cd":
+        Wr, Hr, nr, _ = no.nmf_cd(X, W0, H0, l1, l1, l2, l2, tol=1e-3, max_iter=150)
+        res = slv.fit(W0, H0, solver="cd", l1_G=l1, l2_G=l2, l1_C=l1, l2_C=l2, tol=1e-3, max_iter=150)
+    else:
+        Wr, Hr, nr, _ = no.nmf_mu(X, W0, H0, l1, l1, l2, l2, tol=1e-4, max_iter=150)
+        res = slv.fit(W0, H0, solver="mu", l1_G=l1, l2_G=l2, l1_C=l1, l2_C=l2, tol=1e-4, max_iter=150)
+    assert res.n_iter == nr
+    assert rel_fro(res.G, Wr) < TOL_FACTOR
+    assert rel_fro(res.C, Hr) < TOL_FACTOR
+    np.testing.assert_array_equal(np.argmax(res.C, axis=0), np.argmax(Hr, axis=0))
+
+
+def test_toy_cases_of_reference_tests(kernels, golden):
+    """tests/test_transfer.py of the reference: toy matrices, SC3 filters, pre-processing indices."""
+    from functools import partial
+    from scrna_b200 import NmfClustering
+    from scrna_b200.sc3_clustering_impl import cell_filter, gene_filter
+    g = golden("toys")
+    ids = np.array(['lbl0', 'lbl1', 'lbl2'])
+    nmf = NmfClustering(g["src1"], ids, 2)
+    nmf.add_cell_filter(partial(cell_filter, num_expr_genes=1, non_zero_threshold=1))
+    nmf.add_gene_filter(partial(gene_filter, perc_consensus_genes=0.96, non_zero_threshold=1))
+    nmf.apply()
+    np.testing.assert_array_equal(nmf.pp_data, g["src1"][:2, :4])
+    np.testing.assert_array_equal(nmf.remain_gene_inds, np.arange(2))
+    np.testing.assert_array_equal(nmf.remain_cell_inds, np.arange(4))
+    assert rel_fro(nmf.dictionary @ nmf.data_matrix, g["t1_W"] @ g["t1_H"]) < 1e-3
+    np.testing.assert_array_equal(nmf.cluster_labels, g["t1_labels"])
+
+
+def test_early_exit_after_convergence_is_a_noop(kernels, default_sim, golden):
+    """Iterations enqueued past convergence must not change the factors (device-side done flag)."""
+    g = golden("nmf_source")
+    X = default_sim["src"][:200, :300]
+    W0, H0 = no.nndsvdar_init(X, 4)
+    slv = _solver(kernels, X, 4)
+    r1 = slv.fit(W0, H0, solver="cd", tol=1e-2, max_iter=100, poll=1)
+    r2 = slv.fit(W0, H0, solver="cd", tol=1e-2, max_iter=100, poll=16)
+    assert r1.n_iter == r2.n_iter
+    np.testing.assert_array_equal(r1.G, r2.G)
+    np.testing.assert_array_equal(r1.C, r2.C)

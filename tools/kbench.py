@@ -1,0 +1,97 @@
+"""Kernel micro-benchmark (development tool): times the two X sweeps and whole iterations with CUDA
+events on the launching stream.  X (>= several GB) is far larger than L2, so no flush is needed."""
+import argparse
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+
+from scrna_b200.kernels import default_kernels
+from scrna_b200.nmf_solver import DeviceMatrix, NmfSolver
+from scrna_b200 import _lib
+
+
+def timeit(fn, warm=3, reps=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--genes", type=int, default=20000)
+    ap.add_argument("--cells", type=int, default=100000)
+    ap.add_argument("--k", type=int, nargs="+", default=[8])
+    ap.add_argument("--sa", type=int, nargs="*", default=[])
+    ap.add_argument("--sb", type=int, nargs="*", default=[])
+    args = ap.parse_args()
+    kn = default_kernels()
+    g, n = args.genes, args.cells
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev); gen.manual_seed(1234)
+    ldx = ((n + 31) // 32) * 32
+    X = torch.zeros((g, ldx), dtype=torch.float32, device=dev)
+    rows = 2000
+    for r0 in range(0, g, rows):
+        r1 = min(g, r0 + rows)
+        lam = torch.rand((r1 - r0, 1), device=dev, generator=gen) * 4
+        X[r0:r1, :n] = torch.poisson(lam.expand(r1 - r0, n), generator=gen)
+    dm = DeviceMatrix(X, n)
+    bytes_x = g * ldx * 4
+    out = []
+    for k in args.k:
+        slv = NmfSolver(dm, k, kernels=kn)
+        rng = np.random.RandomState(0)
+        G0 = np.abs(rng.randn(g, k)); C0 = np.abs(rng.randn(k, n))
+        slv._load_factors(G0, C0)
+        kp = slv.kp
+        sa_list = args.sa or [slv.SA]
+        sb_list = args.sb or [slv.SB]
+        for sa in sa_list:
+            PA = torch.empty((sa, g, kp), dtype=torch.float32, device=dev)
+            med, best = timeit(lambda: kn.xht_partial(X, ldx, g, dm.ncols, slv.C32, slv.ldc, kp, PA, sa, None))
+            out.append(dict(kernel="xht_partial", k=k, nsplit=sa, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
+            print(out[-1], flush=True)
+        for sb in sb_list:
+            PB = torch.empty((sb, kp, slv.ldc), dtype=torch.float32, device=dev)
+            med, best = timeit(lambda: kn.wtx_partial(X, ldx, g, dm.ncols, slv.G32, kp, PB, slv.ldc, sb, None))
+            out.append(dict(kernel="wtx_partial", k=k, nsplit=sb, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
+            print(out[-1], flush=True)
+        med, best = timeit(lambda: kn.residual(X, ldx, g, dm.ncols, slv.G32, slv.C32, slv.ldc, kp, 1, slv.res_part, slv.res_out))
+        out.append(dict(kernel="residual_l1", k=k, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
+        print(out[-1], flush=True)
+        # whole iterations
+        for solver in ("mu", "cd"):
+            code = _lib.SOLVER_MU if solver == "mu" else _lib.SOLVER_CD
+            slv._load_factors(G0, C0)
+            perms = np.zeros((64, kp), dtype=np.int32); perms[:, :k] = np.arange(k)
+            slv.perms = torch.from_numpy(perms).to(dev)
+
+            def it():
+                slv._products_for_G(None)
+                slv._update_G(code, 7.5, 2.5, 0, 0, None)
+                slv._half_C(code, 7.5, 2.5, 0, 0, None)
+            med, best = timeit(it, warm=3, reps=10)
+            algo = 2 * bytes_x + 2 * (g + n) * k * 4
+            out.append(dict(kernel="iteration_" + solver, k=k, ms=med, best_ms=best, it_per_s=1000.0 / med,
+                            gbs=algo / med / 1e6))
+            print(out[-1], flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/kbench.json", "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
