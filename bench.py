@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Headline benchmark: NMF multiplicative-update iterations/s on 20 000 genes x 100 000 cells, k=8
+(BASELINE.json metric / configs[2]), cells sharded over the N GPUs of one node.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference          # the reference's CPU arithmetic (sklearn/numpy) timed here
+
+One "step" = one full alternating iteration (gene-factor update, then cell-factor update: two sweeps of
+the resident X) of the whole 20k x 100k problem.  `value` is timed with X already resident in HBM;
+`e2e` goes through the public solver API from pinned HOST buffers (upload of X, transposed copy,
+factor init, 100 iterations, read-back of both factors) and is the headline figure.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+GENES, CELLS, K = 20000, 100000, 8
+L1, L2 = 7.5, 2.5                      # alpha=10, l1_ratio=.75 (cmd_source.py:34-35)
+METRIC = "NMF MU iters/s (20k genes x 100k cells, k=8)"
+UNIT = "iterations/s"
+E2E_ITERS = 100                        # NmfClustering.apply default max_iter (nmf_clustering.py:20)
+CPU_SAMPLE_CELLS = 10000
+CPU_SAMPLE_ITERS = 4
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic counts: restatement of simulation.generate_counts with torch RNGs
+# ---------------------------------------------------------------------------------------------
+def synth_counts(torch, device, genes, cell_begin, cell_end, seed=1234, clusters=8, rows_per_band=2000):
+    """genes x (cell_end-cell_begin) fp32 NB counts on `device`, leading dimension padded to 32.
+    Gene-level parameters depend on `seed` only (identical on every rank); cell-level draws are
+    keyed by the absolute cell index range so that shards tile the same global matrix."""
+    n = cell_end - cell_begin
+    ldx = ((n + 31) // 32) * 32
+    gg = torch.Generator(device=device)
+    gg.manual_seed(seed)
+    mean = torch._standard_gamma(torch.full((genes,), 2.0, device=device), generator=gg) * 0.5  # shape 2, scale .5
+    mean = mean * (0.5 + torch.rand(genes, device=device, generator=gg))
+    de = torch.rand((genes, clusters), device=device, generator=gg) < (
+        0.1 + 0.3 * torch.rand((1, clusters), device=device, generator=gg))
+    lfc = (1.0 + 0.5 * torch.randn((genes, clusters), device=device, generator=gg)) * torch.where(
+        torch.rand((genes, clusters), device=device, generator=gg) < 0.5, -1.0, 1.0)
+    fold = torch.where(de, torch.pow(2.0, lfc), torch.ones_like(lfc))                   # genes x clusters
+    gc = torch.Generator(device=device)
+    gc.manual_seed(seed * 7919 + cell_begin + 1)
+    label = torch.randint(0, clusters, (n,), device=device, generator=gc)
+    size = torch.pow(2.0, 0.5 * torch.randn(n, device=device, generator=gc))
+    X = torch.zeros((genes, ldx), dtype=torch.float32, device=device)
+    for r0 in range(0, genes, rows_per_band):
+        r1 = min(genes, r0 + rows_per_band)
+        mu = mean[r0:r1, None] * fold[r0:r1][:, label] * size[None, :]
+        # NB(n=10, p=10/(10+mu)) drawn as Poisson(Gamma(10, rate=10/mu))
+        shape = torch.full_like(mu, 10.0)
+        lam = torch._standard_gamma(shape, generator=gc) * (mu / 10.0)
+        X[r0:r1, :n] = torch.poisson(lam, generator=gc)
+    return X, n
+
+
+def init_factors(rng, genes, n, k, xmean):
+    avg = np.sqrt(xmean / k)                      # sklearn 'random' init scaling (_nmf.py:296-307)
+    return avg * np.abs(rng.standard_normal((genes, k))), avg * np.abs(rng.standard_normal((k, n)))
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+            sm = sorted(float(r[0]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [nm for i, nm in enumerate(names) if any(r[3 + i].strip() == "Active" for r in rows)]
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                   "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
+        except Exception as e:  # sampling is best effort
+            out["error"] = str(e)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/): the reference's arithmetic on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_mu_iterations(X64, W0, H0, iters):
+    """Times `iters` iterations of the oracle's sklearn-MU restatement (numpy/BLAS, all host threads)."""
+    from oracle import nmf_oracle as no
+    W, H = W0.copy(), H0.copy()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        W = no.mu_update_w(X64, W, H, L1, L2)
+        H = no.mu_update_h(X64, W, H, L1, L2)
+    return (time.perf_counter() - t0) / iters
+
+
+def cpu_sample(sample_cells, seed=1234):
+    """Host fp64 sample of the workload: genes x sample_cells (drawn on the GPU when there is one --
+    data generation is not part of any timed region -- else with the numpy twin of the generator)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            Xd, n = synth_counts(torch, torch.device("cuda", torch.cuda.current_device()), GENES, 0, sample_cells,
+                                 seed=seed)
+            out = Xd[:, :n].to(torch.float64).cpu().numpy()
+            del Xd
+            torch.cuda.empty_cache()
+            return out
+    except Exception:
+        pass
+    rng = np.random.RandomState(seed)
+    mean = rng.gamma(2.0, 0.5, size=(GENES, 1)) * (0.5 + rng.rand(GENES, 1))
+    de = rng.rand(GENES, 8) < (0.1 + 0.3 * rng.rand(1, 8))
+    lfc = (1.0 + 0.5 * rng.randn(GENES, 8)) * np.where(rng.rand(GENES, 8) < 0.5, -1.0, 1.0)
+    fold = np.where(de, 2.0 ** lfc, 1.0)
+    label = rng.randint(0, 8, size=sample_cells)
+    size = 2.0 ** (0.5 * rng.randn(sample_cells))
+    X = np.empty((GENES, sample_cells))
+    for r0 in range(0, GENES, 2000):
+        mu = mean[r0:r0 + 2000] * fold[r0:r0 + 2000][:, label] * size[None, :]
+        X[r0:r0 + 2000] = rng.poisson(rng.gamma(10.0, mu / 10.0))
+    return X
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    X = cpu_sample(CPU_SAMPLE_CELLS)
+    rng = np.random.RandomState(0)
+    W0, H0 = init_factors(rng, GENES, CPU_SAMPLE_CELLS, K, X.mean())
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_mu_iterations(X, W0, H0, 1)
+    steps = max(1, args.steps)
+    sec = cpu_mu_iterations(X, W0, H0, steps)
+    scale = CPU_SAMPLE_CELLS / float(CELLS)
+    value = scale / sec
+    sample = ("%d MU iterations (oracle restatement of sklearn _fit_multiplicative_update, fp64, numpy/BLAS) on "
+              "%d genes x %d cells = 1/%d of the cells; per-iteration time scaled linearly in cells to %d"
+              % (steps, GENES, CPU_SAMPLE_CELLS, int(round(1 / scale)), CELLS))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": sec / scale * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "NMF MU 20000 genes x 100000 cells k=8 (CPU leg on a bounded sample)",
+                   "genes": GENES, "cells": CELLS, "k": K, "l1": L1, "l2": L2, "solver": "mu"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with --nproc-per-node %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from scrna_b200.kernels import default_kernels
+    from scrna_b200.nmf_solver import DeviceMatrix, NmfSolver, TorchDistComm, shard_bounds
+    if world > 1:
+        comm = TorchDistComm()
+    kn = default_kernels()
+
+    genes, cells, k = args.genes, args.cells, args.k
+    c0, c1 = shard_bounds(cells, world, rank)
+    Xd, n_loc = synth_counts(torch, dev, genes, c0, c1)
+    dm = DeviceMatrix(Xd, n_loc)
+    xsum = Xd.sum(dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(xsum)
+    xmean = float(xsum.item()) / (genes * cells)
+    rng = np.random.RandomState(0)
+    G0, C0_full = init_factors(rng, genes, cells, k, xmean)
+    C0 = np.ascontiguousarray(C0_full[:, c0:c1])
+
+    slv = NmfSolver(dm, k, kernels=kn, comm=comm)
+    slv.prepare(G0, C0, solver="mu", l1_G=L1, l2_G=L2, l1_C=L1, l2_C=L2, tol=0.0, max_iter=10 ** 9)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        slv.step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = kn.launches
+    kn.sweep_events = []
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        slv.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = kn.launches - launches0
+    sweeps = kn.sweep_events
+    kn.sweep_events = None
+    clocks = sampler.stop() if rank == 0 else None
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = args.steps / (ms / 1e3)
+
+    # dominant kernel: the X sweep (wtx_partial_kernel<8,4,8>), two launches per iteration
+    sweep_ms = [a.elapsed_time(b) for a, b, _ in sweeps]
+    sweep_bytes = [nb for _, _, nb in sweeps]
+    avg_ms = sum(sweep_ms) / len(sweep_ms)
+    achieved = (sum(sweep_bytes) / len(sweep_bytes)) / (avg_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peaks()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": args.traffic, "kernel": "wtx_partial_kernel<KP=%d>" % slv.kp, "peak_source": peak_src,
+                "launch_ms": avg_ms, "launches_timed": len(sweep_ms),
+                "sweep_share_of_step": sum(sweep_ms) / ms,
+                "algorithmic_bytes_per_launch": sum(sweep_bytes) / len(sweep_bytes),
+                "iteration_algorithmic_gbs": (2 * genes * (c1 - c0) * 4 + 2 * (genes + (c1 - c0)) * k * 4)
+                / (ms / args.steps * 1e-3) / 1e9}
+
+    # ---- end to end through the public API, from pinned host buffers -----------------------------
+    Xh = torch.empty((genes, n_loc), dtype=torch.float32).pin_memory()
+    Xh.copy_(Xd[:, :n_loc])
+    del slv, dm, Xd
+    torch.cuda.empty_cache()
+
+    def e2e_once(iters):
+        barrier()
+        t0 = time.perf_counter()
+        ldx = ((n_loc + 31) // 32) * 32
+        xd = torch.zeros((genes, ldx), dtype=torch.float32, device=dev)
+        xd[:, :n_loc].copy_(Xh, non_blocking=True)
+        s2 = NmfSolver(DeviceMatrix(xd, n_loc), k, kernels=kn, comm=comm)
+        res = s2.fit(G0, C0, solver="mu", l1_G=L1, l2_G=L2, l1_C=L1, l2_C=L2, tol=0.0, max_iter=iters)
+        barrier()
+        dt = time.perf_counter() - t0
+        assert res.G.shape == (genes, k) and res.C.shape == (k, n_loc) and np.isfinite(res.G).all()
+        return dt
+
+    e2e_once(3)
+    dt = e2e_once(E2E_ITERS)
+    tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+    dt = float(tdt.item())
+    h2d = genes * n_loc * 4 + (genes + n_loc) * k * 8
+    d2h = (genes + n_loc) * k * 8 + 64
+    e2e = {"value": E2E_ITERS / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * world / E2E_ITERS,
+           "d2h_bytes_per_step": d2h * world / E2E_ITERS, "iterations_per_call": E2E_ITERS,
+           "seconds_per_call": dt,
+           "what": "NmfSolver(DeviceMatrix(pinned host X -> HBM)).fit(solver='mu', tol=0, max_iter=%d): upload, "
+                   "transposed copy, factor init, iterations, read-back of G and C" % E2E_ITERS}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        Xs = cpu_sample(CPU_SAMPLE_CELLS)
+        Ws, Hs = init_factors(np.random.RandomState(0), genes, CPU_SAMPLE_CELLS, k, Xs.mean())
+        cpu_mu_iterations(Xs, Ws, Hs, 1)
+        sec = cpu_mu_iterations(Xs, Ws, Hs, CPU_SAMPLE_ITERS)
+        scale = CPU_SAMPLE_CELLS / float(cells)
+        cpu_baseline = {"value": scale / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "%d MU iterations of the oracle (sklearn _fit_multiplicative_update restated, fp64, "
+                                  "numpy/BLAS on all host threads) on %d genes x %d cells; scaled linearly in cells to %d"
+                                  % (CPU_SAMPLE_ITERS, genes, CPU_SAMPLE_CELLS, cells)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "NMF MU 20000 genes x 100000 cells k=8, cells sharded over the GPUs "
+                                   "(BASELINE.json configs[2])",
+                       "genes": genes, "cells": cells, "k": k, "solver": "mu", "l1": L1, "l2": L2,
+                       "x_storage": "fp32 genes x cells + resident transposed copy",
+                       "l2_flush": "none needed: each sweep streams %.1f GB per GPU, far larger than the 126 MB L2"
+                                   % (genes * n_loc * 4 / 1e9),
+                       "parallelism": "cells sharded x%d, one all-reduce of %d fp64 per iteration"
+                                      % (world, k * genes + k * k + 4) if world > 1 else "single GPU"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genes", type=int, default=GENES)
+    ap.add_argument("--cells", type=int, default=CELLS)
+    ap.add_argument("--k", type=int, default=K)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="dram bytes per sweep launch from the committed ncu capture (profiles/)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

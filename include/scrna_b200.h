@@ -83,13 +83,15 @@ int scrna_nmf_xht_partial(const float* X, int64_t ldx, int g, int64_t ncols, con
 /* K3 wtx_partial: part[s][t][j] = sum_{i in gene span s} G32[i][t] * X[i][j]   (G^T . X, cells own
  * their output).  Replaces safe_sparse_dot(X.T, W) (_nmf.py:381 via :499-501) / W^T.X of
  * _multiplicative_update_h (_nmf.py:644) / W.T.dot(trg_data) (utils.py:201).
- * part: nsplit x kp x ldc fp32. */
+ * part: nsplit x kp x ldc fp32.  The kernel is orientation-agnostic: called on the resident
+ * transposed copy X^T (cells x genes) with the cell factor's row-major shadow it yields (X.C^T)^T,
+ * i.e. K1 without a cross-lane reduction -- this is the default K1 path. */
 int scrna_nmf_wtx_partial(const float* X, int64_t ldx, int g, int64_t ncols, const float* G32, int kp,
                           float* part, int64_t ldc, int nsplit, int variant,
                           const scrna_nmf_ctrl_t* ctrl, void* stream);
 
-/* Sum the K1 partials over the splits in fixed order into fp64: out[i][t] (g x kp). */
-int scrna_nmf_reduce_rows(const float* part, int nsplit, int g, int kp, double* out,
+/* Sum the K1 partials over the splits in fixed order into fp64, component-major: out[t*ld + i]. */
+int scrna_nmf_reduce_rows(const float* part, int nsplit, int g, int kp, double* out, int64_t ld,
                           const scrna_nmf_ctrl_t* ctrl, void* stream);
 /* Sum the K3 partials over the splits in fixed order into fp64: out[t][j] (kp x ldc). */
 int scrna_nmf_reduce_cols(const float* part, int nsplit, int kp, int64_t ldc, int64_t ncols,
@@ -102,23 +104,30 @@ int scrna_nmf_gram_blocks(void);
 int scrna_nmf_gram(const double* F, int64_t rs, int64_t cs, int64_t rows, int k, int kp,
                    double* partials, double* out, const scrna_nmf_ctrl_t* ctrl, void* stream);
 
-/* K2 / K3-epilogue: update one factor in place (fp64 master F64 and fp32 shadow F32 share the
- * element layout F[r*rs + t*cs], r < rows, t < k).
- *   num  : fp64 products (rows x kp if cs == 1 i.e. gene factor, else kp x ldc i.e. cell factor),
- *          same element layout as F;
+/* K2 / K3-epilogue: update one factor in place.  The fp64 master F64 and the products `num` are
+ * component-major (kp x ld: element [t*ld + r], r < rows, t < k).
  *   gram : kp x kp fp64 Gram of the OTHER factor;
  *   solver MU: F *= num / (F.gram + l1 + l2*F), zero denominators -> float32 eps
  *              (_nmf.py:521-626, 629-723);
  *   solver CD: num -= l1; gram.diag += l2; for t in perm: projected-gradient step
  *              (_nmf.py:369-396 + _cdnmf_fast.pyx:8-38); perm = perms[(ctrl->iter*perm_stride +
  *              perm_offset) * kp .. +k) is the pre-drawn RandomState stream;
+ *   S32  : fp32 row-major shadow (rows x kp, padding components zero) read by the next sweep;
+ *   T32  : optional fp32 component-major shadow (kp x ld) read by scrna_residual / K1 variant 0;
  *   viol_part: scrna_nmf_update_blocks(rows) doubles, per-block sums of |projected gradient|.
  */
 int scrna_nmf_update_blocks(int64_t rows);
-int scrna_nmf_update(int solver, double* F64, float* F32, int64_t rs, int64_t cs, int64_t rows, int k,
-                     int kp, const double* num, const double* gram, double l1, double l2,
-                     const int32_t* perms, int perm_stride, int perm_offset, double* viol_part,
-                     scrna_nmf_ctrl_t* ctrl, void* stream);
+int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t rows, int k, int kp, const double* num,
+                     const double* gram, double l1, double l2, const int32_t* perms, int perm_stride,
+                     int perm_offset, float* S32, float* T32, double* viol_part, scrna_nmf_ctrl_t* ctrl,
+                     void* stream);
+/* Build the fp32 shadows of a component-major fp64 master (initial factors). */
+int scrna_nmf_shadows(const double* F64, int64_t ld, int64_t rows, int k, int kp, float* S32, float* T32,
+                      void* stream);
+/* dst[c][r] = src[r][c] (fp32): the resident transposed copy X^T (cells x genes) that lets K1 run as
+ * the same output-owning stream as K3 (SURVEY.md §7.3 "keep X^T resident"). */
+int scrna_transpose_f32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* dst,
+                        int64_t ld_dst, void* stream);
 
 /* End of one CD iteration: violation = sum(viol_a[0..na)) + sum(viol_b[0..nb)) in fixed order;
  * first iteration stores viol_init; done if viol_init == 0 or violation / viol_init <= tol

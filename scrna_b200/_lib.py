@@ -31,13 +31,15 @@ _SIGNATURES = {
     "scrna_nmf_wtx_splits": [c_int, c_i64, c_int],
     "scrna_nmf_xht_partial": [c_ptr, c_i64, c_int, c_i64, c_ptr, c_i64, c_int, c_ptr, c_int, c_int, c_ptr, c_ptr],
     "scrna_nmf_wtx_partial": [c_ptr, c_i64, c_int, c_i64, c_ptr, c_int, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr],
-    "scrna_nmf_reduce_rows": [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr],
+    "scrna_nmf_reduce_rows": [c_ptr, c_int, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr],
     "scrna_nmf_reduce_cols": [c_ptr, c_int, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "scrna_nmf_gram_blocks": [],
     "scrna_nmf_gram": [c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_nmf_update_blocks": [c_i64],
-    "scrna_nmf_update": [c_int, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_dbl, c_dbl,
-                         c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr],
+    "scrna_nmf_update": [c_int, c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_dbl, c_dbl,
+                         c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "scrna_nmf_shadows": [c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr],
+    "scrna_transpose_f32": [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr],
     "scrna_nmf_iter_end": [c_ptr, c_ptr, c_int, c_ptr, c_int, c_dbl, c_int, c_ptr],
     "scrna_nmf_ctrl_reset": [c_ptr, c_ptr],
     "scrna_cast_f64_f32": [c_ptr, c_ptr, c_i64, c_ptr],

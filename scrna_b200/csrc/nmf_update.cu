@@ -23,6 +23,21 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int nspli
   }
 }
 
+// K1 (row-major partials nsplit x g x kp) -> component-major fp64 out[t*ld + i]
+__global__ void reduce_rows_t_kernel(const float* __restrict__ part, int nsplit, int g, int kp,
+                                     double* __restrict__ out, int64_t ld, const NmfCtrl* __restrict__ ctrl) {
+  if (ctrl_done(ctrl)) return;
+  const int64_t count = (int64_t)g * kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int p = 0; p < nsplit; ++p) s += (double)part[(int64_t)p * count + i];
+    const int64_t row = i / kp;
+    const int t = (int)(i - row * kp);
+    out[(int64_t)t * ld + row] = s;
+  }
+}
+
 // ---- Gram of a factor: out[a][b] = sum_r F[r*rs + a*cs] * F[r*rs + b*cs] -----------------------
 constexpr int GRAM_TILE = 64;     // rows per smem tile
 constexpr int GRAM_THREADS = 256;
@@ -90,15 +105,19 @@ __global__ void gram_final_kernel(const double* __restrict__ partials, int nblk,
 }
 
 // ---- factor update ---------------------------------------------------------------------------
-// One thread per factor row r (a gene of G, or a cell of C).  The row's k entries live in shared
-// memory as sw[t * UPD_THREADS + tid] so that the CD sweep can index them by the (uniform)
-// permuted component without spilling registers; the k x k Gram is broadcast from shared memory.
+// One thread per factor row r (a gene of G, or a cell of C).  Master F64 and the products `num` are
+// component-major (kp x ld, element [t*ld + r]) so consecutive threads read consecutive addresses.
+// The row's k entries live in shared memory as sw[t * UPD_THREADS + tid] so that the CD sweep can
+// index them by the (uniform) permuted component without spilling; the k x k Gram is broadcast from
+// shared memory.  Outputs: master, fp32 row-major shadow S32 (rows x kp, what the streaming sweep
+// broadcasts from smem) and optionally the fp32 component-major shadow T32 (kp x ld).
 template <int SOLVER>
 __global__ void __launch_bounds__(UPD_THREADS)
-update_kernel(double* __restrict__ F64, float* __restrict__ F32, int64_t rs, int64_t cs, int64_t rows,
-              int k, int kp, const double* __restrict__ num, const double* __restrict__ gram, double l1,
-              double l2, const int32_t* __restrict__ perms, int perm_stride, int perm_offset,
-              double* __restrict__ viol_part, NmfCtrl* __restrict__ ctrl) {
+update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
+              const double* __restrict__ num, const double* __restrict__ gram, double l1, double l2,
+              const int32_t* __restrict__ perms, int perm_stride, int perm_offset,
+              float* __restrict__ S32, float* __restrict__ T32, double* __restrict__ viol_part,
+              NmfCtrl* __restrict__ ctrl) {
   if (ctrl_done(ctrl)) return;
   extern __shared__ double smem[];
   double* sg = smem;                         // kp*kp Gram
@@ -123,7 +142,7 @@ update_kernel(double* __restrict__ F64, float* __restrict__ F32, int64_t rs, int
   bool nan_seen = false;
   if (live) {
     for (int t = 0; t < k; ++t) {
-      const int64_t e = r * rs + (int64_t)t * cs;
+      const int64_t e = (int64_t)t * ld + r;
       sw[t * UPD_THREADS + tid] = F64[e];
       sn[t * UPD_THREADS + tid] = num[e];
     }
@@ -136,16 +155,9 @@ update_kernel(double* __restrict__ F64, float* __restrict__ F32, int64_t rs, int
         if (l1 > 0.0) den += l1;
         if (l2 > 0.0) den = den + l2 * w;
         if (den == 0.0) den = (double)kEpsMU;
-        const double v = w * (sn[t * UPD_THREADS + tid] / den);
-        sn[t * UPD_THREADS + tid] = v;  // numerator no longer needed: reuse as the new value
+        sn[t * UPD_THREADS + tid] = w * (sn[t * UPD_THREADS + tid] / den);  // numerator slot := new value
       }
-      for (int t = 0; t < k; ++t) {
-        const double v = sn[t * UPD_THREADS + tid];
-        nan_seen |= (v != v);
-        const int64_t e = r * rs + (int64_t)t * cs;
-        F64[e] = v;
-        F32[e] = (float)v;
-      }
+      for (int t = 0; t < k; ++t) sw[t * UPD_THREADS + tid] = sn[t * UPD_THREADS + tid];
     } else {
       // _update_cdnmf_fast with HHt.diag += l2 and XHt -= l1 (_nmf.py:383-388)
       for (int s = 0; s < k; ++s) {
@@ -162,12 +174,23 @@ update_kernel(double* __restrict__ F64, float* __restrict__ F32, int64_t rs, int
         const double hess = sg[t * kp + t] + l2;
         if (hess != 0.0) sw[t * UPD_THREADS + tid] = fmax(w - grad / hess, 0.0);
       }
-      for (int t = 0; t < k; ++t) {
-        const double v = sw[t * UPD_THREADS + tid];
-        nan_seen |= (v != v);
-        const int64_t e = r * rs + (int64_t)t * cs;
-        F64[e] = v;
-        F32[e] = (float)v;
+    }
+    for (int t = 0; t < k; ++t) {
+      const double v = sw[t * UPD_THREADS + tid];
+      nan_seen |= (v != v);
+      const int64_t e = (int64_t)t * ld + r;
+      F64[e] = v;
+      if (T32) T32[e] = (float)v;
+    }
+    if (S32) {
+      float* srow = S32 + r * kp;
+      for (int t = 0; t < kp; t += 4) {
+        float4 o;
+        o.x = (t + 0 < k) ? (float)sw[(t + 0) * UPD_THREADS + tid] : 0.f;
+        o.y = (t + 1 < k) ? (float)sw[(t + 1) * UPD_THREADS + tid] : 0.f;
+        o.z = (t + 2 < k) ? (float)sw[(t + 2) * UPD_THREADS + tid] : 0.f;
+        o.w = (t + 3 < k) ? (float)sw[(t + 3) * UPD_THREADS + tid] : 0.f;
+        *reinterpret_cast<float4*>(srow + t) = o;
       }
     }
   }
@@ -176,6 +199,38 @@ update_kernel(double* __restrict__ F64, float* __restrict__ F32, int64_t rs, int
   if (tid == 0) {
     if (viol_part) viol_part[blockIdx.x] = bsum;
     if (snan && ctrl) atomicOr(&ctrl->flags, SCRNA_FLAG_NAN);
+  }
+}
+
+// fp64 component-major master (kp x ld) -> fp32 row-major shadow (rows x kp) [+ component-major shadow]
+__global__ void shadows_kernel(const double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
+                               float* __restrict__ S32, float* __restrict__ T32) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  for (int t = 0; t < kp; ++t) {
+    const float v = t < k ? (float)F64[(int64_t)t * ld + r] : 0.f;
+    if (S32) S32[r * kp + t] = v;
+    if (T32 && t < k) T32[(int64_t)t * ld + r] = v;
+  }
+}
+
+// dst[c][r] = src[r][c] (fp32), dst padding columns [rows, ld_dst) zeroed by the caller
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int64_t cols,
+                 float* __restrict__ dst, int64_t ld_dst) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int64_t r = r0 + ty + i, c = c0 + tx;
+    tile[ty + i][tx] = (r < rows && c < cols) ? src[r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int64_t c = c0 + ty + i, r = r0 + tx;
+    if (c < cols && r < rows) dst[c * ld_dst + r] = tile[tx][ty + i];
   }
 }
 
@@ -258,12 +313,12 @@ extern "C" int scrna_device_info(int* sm_count, int* max_smem_per_block, int* cc
   return last_launch_status();
 }
 
-extern "C" int scrna_nmf_reduce_rows(const float* part, int nsplit, int g, int kp, double* out,
+extern "C" int scrna_nmf_reduce_rows(const float* part, int nsplit, int g, int kp, double* out, int64_t ld,
                                      const scrna_nmf_ctrl_t* ctrl, void* stream) {
-  if (!part || !out || nsplit <= 0 || g <= 0 || kp <= 0) return SCRNA_ERR_BADARG;
+  if (!part || !out || nsplit <= 0 || g <= 0 || kp <= 0 || ld < g) return SCRNA_ERR_BADARG;
   const int64_t count = (int64_t)g * kp;
-  reduce_partials_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(
-      part, nsplit, count, count, out, (const NmfCtrl*)ctrl);
+  reduce_rows_t_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(
+      part, nsplit, g, kp, out, ld, (const NmfCtrl*)ctrl);
   return last_launch_status();
 }
 
@@ -292,11 +347,11 @@ extern "C" int scrna_nmf_gram(const double* F, int64_t rs, int64_t cs, int64_t r
 
 extern "C" int scrna_nmf_update_blocks(int64_t rows) { return (int)ceil_div(rows, UPD_THREADS); }
 
-extern "C" int scrna_nmf_update(int solver, double* F64, float* F32, int64_t rs, int64_t cs, int64_t rows,
-                                int k, int kp, const double* num, const double* gram, double l1, double l2,
-                                const int32_t* perms, int perm_stride, int perm_offset, double* viol_part,
-                                scrna_nmf_ctrl_t* ctrl, void* stream) {
-  if (!F64 || !F32 || !num || !gram || rows <= 0 || k <= 0 || k > kp || kp > SCRNA_MAX_K)
+extern "C" int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t rows, int k, int kp,
+                                const double* num, const double* gram, double l1, double l2,
+                                const int32_t* perms, int perm_stride, int perm_offset, float* S32, float* T32,
+                                double* viol_part, scrna_nmf_ctrl_t* ctrl, void* stream) {
+  if (!F64 || !num || !gram || rows <= 0 || ld < rows || k <= 0 || k > kp || kp > SCRNA_MAX_K || (kp & 3))
     return SCRNA_ERR_BADARG;
   const size_t smem = ((size_t)kp * kp + 2 * (size_t)k * UPD_THREADS) * sizeof(double);
   const int nblk = (int)ceil_div(rows, UPD_THREADS);
@@ -308,15 +363,32 @@ extern "C" int scrna_nmf_update(int solver, double* F64, float* F32, int64_t rs,
     attr_set = true;
   }
   if (solver == SCRNA_SOLVER_MU)
-    update_kernel<SCRNA_SOLVER_MU><<<nblk, UPD_THREADS, smem, st>>>(F64, F32, rs, cs, rows, k, kp, num, gram, l1, l2,
-                                                                  perms, perm_stride, perm_offset, viol_part,
+    update_kernel<SCRNA_SOLVER_MU><<<nblk, UPD_THREADS, smem, st>>>(F64, ld, rows, k, kp, num, gram, l1, l2, perms,
+                                                                  perm_stride, perm_offset, S32, T32, viol_part,
                                                                   (NmfCtrl*)ctrl);
   else if (solver == SCRNA_SOLVER_CD)
-    update_kernel<SCRNA_SOLVER_CD><<<nblk, UPD_THREADS, smem, st>>>(F64, F32, rs, cs, rows, k, kp, num, gram, l1, l2,
-                                                                  perms, perm_stride, perm_offset, viol_part,
+    update_kernel<SCRNA_SOLVER_CD><<<nblk, UPD_THREADS, smem, st>>>(F64, ld, rows, k, kp, num, gram, l1, l2, perms,
+                                                                  perm_stride, perm_offset, S32, T32, viol_part,
                                                                   (NmfCtrl*)ctrl);
   else
     return SCRNA_ERR_BADARG;
+  return last_launch_status();
+}
+
+extern "C" int scrna_nmf_shadows(const double* F64, int64_t ld, int64_t rows, int k, int kp, float* S32,
+                                 float* T32, void* stream) {
+  if (!F64 || rows <= 0 || ld < rows || k <= 0 || k > kp) return SCRNA_ERR_BADARG;
+  shadows_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(F64, ld, rows, k, kp, S32, T32);
+  return last_launch_status();
+}
+
+extern "C" int scrna_transpose_f32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* dst,
+                                   int64_t ld_dst, void* stream) {
+  if (!src || !dst || rows <= 0 || cols <= 0 || cols > ld_src || rows > ld_dst) return SCRNA_ERR_BADARG;
+  const int64_t by = ceil_div(rows, 32);
+  if (by > 65535) return SCRNA_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)by);
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, rows, cols, dst, ld_dst);
   return last_launch_status();
 }
 

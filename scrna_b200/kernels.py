@@ -13,7 +13,8 @@ class CudaKernels:
     def __init__(self):
         self.torch = _lib.require_cuda()
         _lib.load()
-        self.launches = 0  # number of C-ABI kernel-launching calls issued (bench.py: gpu_launches)
+        self.launches = 0  # number of kernels launched through the C ABI (bench.py: gpu_launches)
+        self.sweep_events = None  # bench.py sets a list: (start, stop, X bytes) CUDA events per sweep launch
 
     def _s(self):
         return self.torch.cuda.current_stream().cuda_stream
@@ -43,10 +44,18 @@ class CudaKernels:
         self._call("scrna_nmf_xht_partial", X, ldx, g, ncols, C32, ldc, kp, part, nsplit, variant, ctrl, self._s())
 
     def wtx_partial(self, X, ldx, g, ncols, G32, kp, part, ldc, nsplit, ctrl, variant=0):
+        ev = self.sweep_events
+        if ev is not None:
+            a = self.torch.cuda.Event(enable_timing=True)
+            b = self.torch.cuda.Event(enable_timing=True)
+            a.record()
         self._call("scrna_nmf_wtx_partial", X, ldx, g, ncols, G32, kp, part, ldc, nsplit, variant, ctrl, self._s())
+        if ev is not None:
+            b.record()
+            ev.append((a, b, int(g) * int(ncols) * 4))
 
-    def reduce_rows(self, part, nsplit, g, kp, out, ctrl):
-        self._call("scrna_nmf_reduce_rows", part, nsplit, g, kp, out, ctrl, self._s())
+    def reduce_rows(self, part, nsplit, g, kp, out, ld, ctrl):
+        self._call("scrna_nmf_reduce_rows", part, nsplit, g, kp, out, ld, ctrl, self._s())
 
     def reduce_cols(self, part, nsplit, kp, ldc, ncols, out, ctrl):
         self._call("scrna_nmf_reduce_cols", part, nsplit, kp, ldc, ncols, out, ctrl, self._s())
@@ -55,10 +64,16 @@ class CudaKernels:
         self.launches += 1  # two kernels per call
         self._call("scrna_nmf_gram", F64, rs, cs, rows, k, kp, partials, out, ctrl, self._s())
 
-    def update(self, solver, F64, F32, rs, cs, rows, k, kp, num, gram, l1, l2, perms, perm_stride, perm_offset,
+    def update(self, solver, F64, ld, rows, k, kp, num, gram, l1, l2, perms, perm_stride, perm_offset, S32, T32,
                viol_part, ctrl):
-        self._call("scrna_nmf_update", solver, F64, F32, rs, cs, rows, k, kp, num, gram, float(l1), float(l2),
-                   perms, perm_stride, perm_offset, viol_part, ctrl, self._s())
+        self._call("scrna_nmf_update", solver, F64, ld, rows, k, kp, num, gram, float(l1), float(l2),
+                   perms, perm_stride, perm_offset, S32, T32, viol_part, ctrl, self._s())
+
+    def shadows(self, F64, ld, rows, k, kp, S32, T32):
+        self._call("scrna_nmf_shadows", F64, ld, rows, k, kp, S32, T32, self._s())
+
+    def transpose(self, src, ld_src, rows, cols, dst, ld_dst):
+        self._call("scrna_transpose_f32", src, ld_src, rows, cols, dst, ld_dst, self._s())
 
     def iter_end(self, ctrl, viol_a, na, viol_b, nb, tol, max_iter):
         self._call("scrna_nmf_iter_end", ctrl, viol_a, na, viol_b, nb, float(tol), int(max_iter), self._s())

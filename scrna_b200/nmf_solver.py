@@ -4,12 +4,12 @@ One iteration (sklearn `_fit_coordinate_descent` loop body, SP/sklearn/decomposi
 or `_fit_multiplicative_update`, _nmf.py:826-864) is, for the gene factor G (g x k) and the cell
 factor C (k x n):
 
-    K1  xht_partial(X, C32)  -> reduce_rows -> R.xht (g x kp fp64)         one sweep of X
+    K1  sweep(X^T, Cs32)     -> reduce      -> R.xht (kp x ldg fp64)       one sweep (of the X^T copy)
     K4  gram(C64)            -> R.cct (kp x kp fp64)
         [all-reduce R over the cell shards: the ONLY per-iteration collective]
     K2  update(G | R.xht, R.cct)            (MU ratio or CD sweep; fp64; writes the fp32 shadow)
     K4  gram(G64)            -> gtg
-    K3  wtx_partial(X, G32)  -> reduce_cols -> nb (kp x ldc fp64)          second sweep of X
+    K3  sweep(X, Gs32)       -> reduce      -> nb (kp x ldn fp64)          second sweep (of X)
         update(C | nb, gtg)                 (cells are local to the shard: no communication)
         iter_end                            (device-side stop rule, _nmf.py:504-516)
 
@@ -86,10 +86,14 @@ class DeviceMatrix:
         torch.cuda.current_stream().synchronize()
         return cls(out, n)
 
-    @classmethod
-    def from_device(cls, t32, n=None):
-        assert t32.dtype == t32.new_empty(0, dtype=t32.dtype).dtype and t32.dim() == 2
-        return cls(t32, t32.shape[1] if n is None else n)
+    def transposed(self, kernels):
+        """Resident transposed copy: cells x genes fp32, leading dimension padded to 32 genes."""
+        torch = kernels.torch
+        ldg = round_up(self.g, 32)
+        out = torch.zeros((max(self.n, 1), ldg), dtype=torch.float32, device=self.data.device)
+        if self.n > 0:
+            kernels.transpose(self.data, self.ldx, self.g, self.n, out, ldg)
+        return DeviceMatrix(out, self.g)
 
 
 class TorchDistComm:
@@ -117,7 +121,14 @@ class NmfResult:
 
 
 class NmfSolver:
-    def __init__(self, X, k, kernels=None, comm=None):
+    """Device state of one NMF problem on one cell shard.
+
+    Layouts: X genes x cells fp32 (+ the resident transposed copy X^T unless
+    transpose_copy=False); factor masters component-major fp64 (G64: kp x ldg, C64: kp x ldn);
+    fp32 row-major shadows Gs32 (g x kp) / Cs32 (n x kp) that the sweeps broadcast from shared
+    memory, and the component-major fp32 shadow Ct32 for the residual kernel."""
+
+    def __init__(self, X, k, kernels=None, comm=None, transpose_copy=True):
         if kernels is None:
             from .kernels import default_kernels
             kernels = default_kernels()
@@ -129,27 +140,35 @@ class NmfSolver:
         self.comm = comm if (comm is not None and comm.world > 1) else None
         t = self.torch
         dev = X.data.device
-        g, kp, ldc = X.g, self.kp, X.ldx
-        self.ldc = ldc
+        g, n, kp = X.g, max(X.n, 1), self.kp
+        self.ldn = ldn = X.ldx
+        self.ldg = ldg = round_up(g, 32)
+        self.gcols = round_up(g, 4)
         f64, f32 = t.float64, t.float32
-        self.G64 = t.zeros((g, kp), dtype=f64, device=dev)
-        self.G32 = t.zeros((g, kp), dtype=f32, device=dev)
-        self.C64 = t.zeros((kp, ldc), dtype=f64, device=dev)
-        self.C32 = t.zeros((kp, ldc), dtype=f32, device=dev)
-        self.SA = kernels.xht_splits(g, X.ncols, kp)
+        self.XT = X.transposed(kernels) if transpose_copy else None
+        self.G64 = t.zeros((kp, ldg), dtype=f64, device=dev)
+        self.Gs32 = t.zeros((g, kp), dtype=f32, device=dev)
+        self.C64 = t.zeros((kp, ldn), dtype=f64, device=dev)
+        self.Cs32 = t.zeros((n, kp), dtype=f32, device=dev)
+        self.Ct32 = t.zeros((kp, ldn), dtype=f32, device=dev)
+        if self.XT is not None:
+            self.SA = kernels.wtx_splits(n, self.gcols, kp)
+            self.PA = t.zeros((self.SA, kp, ldg), dtype=f32, device=dev)
+        else:
+            self.SA = kernels.xht_splits(g, X.ncols, kp)
+            self.PA = t.zeros((self.SA, g, kp), dtype=f32, device=dev)
         self.SB = kernels.wtx_splits(g, X.ncols, kp)
-        self.PA = t.empty((self.SA, g, kp), dtype=f32, device=dev)
-        self.PB = t.empty((self.SB, kp, ldc), dtype=f32, device=dev)
-        # all-reduce payload: [ X.C^T (g*kp) | C.C^T (kp*kp) | 4 scalars ]
-        self.R = t.zeros(g * kp + kp * kp + 4, dtype=f64, device=dev)
-        self.R_xht = self.R[: g * kp]
-        self.R_cct = self.R[g * kp: g * kp + kp * kp]
-        self.R_scal = self.R[g * kp + kp * kp:]
-        self.NB = t.zeros((kp, ldc), dtype=f64, device=dev)
+        self.PB = t.zeros((self.SB, kp, ldn), dtype=f32, device=dev)
+        # all-reduce payload: [ (X.C^T)^T (kp*ldg) | C.C^T (kp*kp) | 4 scalars ]
+        self.R = t.zeros(kp * ldg + kp * kp + 4, dtype=f64, device=dev)
+        self.R_xht = self.R[: kp * ldg]
+        self.R_cct = self.R[kp * ldg: kp * ldg + kp * kp]
+        self.R_scal = self.R[kp * ldg + kp * kp:]
+        self.NB = t.zeros((kp, ldn), dtype=f64, device=dev)
         self.gtg = t.zeros(kp * kp, dtype=f64, device=dev)
         self.gram_part = t.zeros(kernels.gram_blocks() * kp * kp, dtype=f64, device=dev)
         self.nblkG = kernels.update_blocks(g)
-        self.nblkC = kernels.update_blocks(max(X.n, 1))
+        self.nblkC = kernels.update_blocks(n)
         self.violG = t.zeros(self.nblkG, dtype=f64, device=dev)
         self.violC = t.zeros(self.nblkC, dtype=f64, device=dev)
         self.ctrl = t.zeros(16, dtype=t.int32, device=dev)
@@ -160,18 +179,18 @@ class NmfSolver:
     # ---- helpers ------------------------------------------------------------------------------
     def _load_factors(self, G0, C0):
         t = self.torch
-        X, k = self.X, self.k
-        G0 = np.ascontiguousarray(G0, dtype=np.float64)
+        X, k, kp = self.X, self.k, self.kp
+        G0 = np.ascontiguousarray(np.asarray(G0, dtype=np.float64).T)
         C0 = np.ascontiguousarray(C0, dtype=np.float64)
-        if G0.shape != (X.g, k) or C0.shape != (k, X.n):
-            raise ValueError("init shapes %s / %s do not match X %dx%d, k=%d" % (G0.shape, C0.shape, X.g, X.n, k))
+        if G0.shape != (k, X.g) or C0.shape != (k, X.n):
+            raise ValueError("init shapes do not match X %dx%d, k=%d" % (X.g, X.n, k))
         dev = X.data.device
         self.G64.zero_()
         self.C64.zero_()
-        self.G64[:, :k].copy_(t.from_numpy(G0).to(dev))
+        self.G64[:k, : X.g].copy_(t.from_numpy(G0).to(dev))
         self.C64[:k, : X.n].copy_(t.from_numpy(C0).to(dev))
-        self.kn.cast_f64_f32(self.G64, self.G32, self.G64.numel())
-        self.kn.cast_f64_f32(self.C64, self.C32, self.C64.numel())
+        self.kn.shadows(self.G64, self.ldg, X.g, k, kp, self.Gs32, None)
+        self.kn.shadows(self.C64, self.ldn, max(X.n, 1), k, kp, self.Cs32, self.Ct32)
 
     def read_ctrl(self):
         raw = self.ctrl.cpu().numpy()
@@ -182,52 +201,53 @@ class NmfSolver:
 
     def factors_to_host(self):
         X, k = self.X, self.k
-        G = self.G64[:, :k].cpu().numpy().copy()
+        G = np.ascontiguousarray(self.G64[:k, : X.g].cpu().numpy().T)
         C = self.C64[:k, : X.n].cpu().numpy().copy()
         return G, C
 
     # ---- the two half steps -------------------------------------------------------------------
     def _products_for_G(self, ctrl):
-        """R.xht = X.C^T (this shard), R.cct = C.C^T (this shard), then the all-reduce."""
-        kn, X = self.kn, self.X
-        kn.xht_partial(X.data, X.ldx, X.g, X.ncols, self.C32, self.ldc, self.kp, self.PA, self.SA, ctrl)
-        kn.reduce_rows(self.PA, self.SA, X.g, self.kp, self.R_xht, ctrl)
-        kn.gram(self.C64, 1, self.ldc, max(X.n, 1), self.k, self.kp, self.gram_part, self.R_cct, ctrl)
+        """R.xht = (X.C^T)^T (this shard), R.cct = C.C^T (this shard); the all-reduce follows."""
+        kn, X, kp = self.kn, self.X, self.kp
+        if self.XT is not None:
+            XT = self.XT
+            kn.wtx_partial(XT.data, XT.ldx, XT.g, self.gcols, self.Cs32, kp, self.PA, self.ldg, self.SA, ctrl)
+            kn.reduce_cols(self.PA, self.SA, kp, self.ldg, self.gcols, self.R_xht, ctrl)
+        else:
+            kn.xht_partial(X.data, X.ldx, X.g, X.ncols, self.Ct32, self.ldn, kp, self.PA, self.SA, ctrl)
+            kn.reduce_rows(self.PA, self.SA, X.g, kp, self.R_xht, self.ldg, ctrl)
+        kn.gram(self.C64, 1, self.ldn, max(X.n, 1), self.k, kp, self.gram_part, self.R_cct, ctrl)
 
     def _allreduce_R(self):
         if self.comm is not None:
             self.comm.all_reduce(self.R)
 
     def _update_G(self, solver, l1, l2, stride, offset, ctrl):
-        self.kn.update(solver, self.G64, self.G32, self.kp, 1, self.X.g, self.k, self.kp, self.R_xht, self.R_cct,
-                       l1, l2, self.perms, stride, offset, self.violG, ctrl)
+        self.kn.update(solver, self.G64, self.ldg, self.X.g, self.k, self.kp, self.R_xht, self.R_cct, l1, l2,
+                       self.perms, stride, offset, self.Gs32, None, self.violG, ctrl)
 
     def _half_C(self, solver, l1, l2, stride, offset, ctrl):
-        kn, X = self.kn, self.X
-        kn.gram(self.G64, self.kp, 1, X.g, self.k, self.kp, self.gram_part, self.gtg, ctrl)
-        kn.wtx_partial(X.data, X.ldx, X.g, X.ncols, self.G32, self.kp, self.PB, self.ldc, self.SB, ctrl)
-        kn.reduce_cols(self.PB, self.SB, self.kp, self.ldc, X.ncols, self.NB, ctrl)
-        kn.update(solver, self.C64, self.C32, 1, self.ldc, max(X.n, 1), self.k, self.kp, self.NB, self.gtg,
-                  l1, l2, self.perms, stride, offset, self.violC, ctrl)
+        kn, X, kp = self.kn, self.X, self.kp
+        kn.gram(self.G64, 1, self.ldg, X.g, self.k, kp, self.gram_part, self.gtg, ctrl)
+        kn.wtx_partial(X.data, X.ldx, X.g, X.ncols, self.Gs32, kp, self.PB, self.ldn, self.SB, ctrl)
+        kn.reduce_cols(self.PB, self.SB, kp, self.ldn, X.ncols, self.NB, ctrl)
+        kn.update(solver, self.C64, self.ldn, max(X.n, 1), self.k, kp, self.NB, self.gtg, l1, l2,
+                  self.perms, stride, offset, self.Cs32, self.Ct32, self.violC, ctrl)
 
     def frobenius_error(self):
         """||X - G.C||_F over all shards (sklearn _beta_divergence(..., square_root=True))."""
         X = self.X
-        self.kn.residual(X.data, X.ldx, X.g, X.ncols, self.G32, self.C32, self.ldc, self.kp, 2, self.res_part,
+        self.kn.residual(X.data, X.ldx, X.g, X.ncols, self.Gs32, self.Ct32, self.ldn, self.kp, 2, self.res_part,
                          self.res_out)
         if self.comm is not None:
             self.comm.all_reduce(self.res_out)
         return math.sqrt(max(float(self.res_out.cpu()[0]), 0.0))
 
     # ---- public -------------------------------------------------------------------------------
-    def fit(self, G0, C0, solver="cd", l1_G=0.0, l2_G=0.0, l1_C=0.0, l2_C=0.0, tol=1e-4, max_iter=200,
-            update_G=True, update_C=True, first="G", seed=0, shuffle=True, perms=None, poll=4,
-            to_host=True):
-        """Run the alternating updates from (G0, C0).  Returns NmfResult.
-
-        solver 'cd' reproduces sklearn's coordinate descent (stop: violation/violation_init <= tol),
-        solver 'mu' sklearn's multiplicative update (stop: every 10 iterations,
-        (previous_error - error)/error_at_init < tol; tol=0 runs exactly max_iter iterations)."""
+    def prepare(self, G0, C0, solver="cd", l1_G=0.0, l2_G=0.0, l1_C=0.0, l2_C=0.0, tol=1e-4, max_iter=200,
+                update_G=True, update_C=True, first="G", seed=0, shuffle=True, perms=None):
+        """Load the factors, pre-draw the permutation stream and build the per-iteration launch
+        sequence (`self.step()`); nothing is iterated yet."""
         if solver not in ("cd", "mu"):
             raise ValueError("solver must be 'cd' or 'mu'")
         if first not in ("G", "C"):
@@ -266,13 +286,7 @@ class NmfSolver:
             self._products_for_G(None)
             self._allreduce_R()
         if not update_G:
-            kn.gram(self.G64, self.kp, 1, self.X.g, self.k, self.kp, self.gram_part, self.gtg, None)
-
-        errors = None
-        error_at_init = previous_error = None
-        if solver == "mu" and tol > 0:
-            error_at_init = previous_error = self.frobenius_error()
-            errors = [(0, error_at_init)]
+            kn.gram(self.G64, 1, self.ldg, self.X.g, self.k, self.kp, self.gram_part, self.gtg, None)
 
         def one_iteration():
             if first == "G":
@@ -303,10 +317,29 @@ class NmfSolver:
                 vb, nb = None, 0
             kn.iter_end(ctrl, va, na, vb, nb, cd_tol, max_iter)
 
+        self.step = one_iteration
+        self._plan = dict(solver=solver, tol=float(tol), max_iter=max_iter)
+
+    def fit(self, G0, C0, solver="cd", l1_G=0.0, l2_G=0.0, l1_C=0.0, l2_C=0.0, tol=1e-4, max_iter=200,
+            update_G=True, update_C=True, first="G", seed=0, shuffle=True, perms=None, poll=4,
+            to_host=True):
+        """Run the alternating updates from (G0, C0).  Returns NmfResult.
+
+        solver 'cd' reproduces sklearn's coordinate descent (stop: violation/violation_init <= tol),
+        solver 'mu' sklearn's multiplicative update (stop: every 10 iterations,
+        (previous_error - error)/error_at_init < tol; tol=0 runs exactly max_iter iterations)."""
+        self.prepare(G0, C0, solver=solver, l1_G=l1_G, l2_G=l2_G, l1_C=l1_C, l2_C=l2_C, tol=tol,
+                     max_iter=max_iter, update_G=update_G, update_C=update_C, first=first, seed=seed,
+                     shuffle=shuffle, perms=perms)
+        max_iter = int(max_iter)
+        errors = None
+        error_at_init = previous_error = None
+        if solver == "mu" and tol > 0:
+            error_at_init = previous_error = self.frobenius_error()
+            errors = [(0, error_at_init)]
         n_done = 0
-        state = None
         while n_done < max_iter:
-            one_iteration()
+            self.step()
             n_done += 1
             if solver == "mu":
                 if tol > 0 and n_done % 10 == 0:
@@ -316,8 +349,7 @@ class NmfSolver:
                         break
                     previous_error = error
             elif n_done % poll == 0 or n_done == max_iter:
-                state = self.read_ctrl()
-                if state["done"]:
+                if self.read_ctrl()["done"]:
                     break
         state = self.read_ctrl()
         n_iter = state["n_iter"] if (solver == "cd" and state["done"]) else n_done

@@ -42,7 +42,7 @@ class TransferSession:
         self.WtW = t.zeros(kp * kp, dtype=f64, device=dev)
         self.gram_part = t.zeros(kernels.gram_blocks() * kp * kp, dtype=f64, device=dev)
         self.SB = kernels.wtx_splits(X.g, X.ncols, kp)
-        self.PB = t.empty((self.SB, kp, ldc), dtype=f32, device=dev)
+        self.PB = t.zeros((self.SB, kp, ldc), dtype=f32, device=dev)
         self.res_part = t.zeros(max(1, kernels.residual_blocks(X.ncols, kp)), dtype=f64, device=dev)
         self.res_out = t.zeros(1, dtype=f64, device=dev)
         self.ctrl = t.zeros(16, dtype=t.int32, device=dev)

@@ -21,38 +21,42 @@ def _recon_err(X, W, H):
     return np.linalg.norm(X - W @ H) / np.linalg.norm(X)
 
 
-def _solver(kernels, X, k):
+def _solver(kernels, X, k, transpose_copy=True):
     from scrna_b200.nmf_solver import DeviceMatrix, NmfSolver
-    return NmfSolver(DeviceMatrix.from_host(X, kernels), k, kernels=kernels)
+    return NmfSolver(DeviceMatrix.from_host(X, kernels), k, kernels=kernels, transpose_copy=transpose_copy)
 
 
+@pytest.mark.parametrize("transpose_copy", [True, False])
 @pytest.mark.parametrize("g,n,k", [(1000, 1000, 8), (333, 517, 7), (64, 4100, 5), (2500, 130, 16),
                                    (129, 257, 33), (40, 36, 3), (700, 900, 50), (5, 7, 2)])
-def test_sweeps_match_fp64_products(kernels, g, n, k):
+def test_sweeps_match_fp64_products(kernels, g, n, k, transpose_copy):
     torch = kernels.torch
     rng = np.random.RandomState(g + n + k)
     X = rng.poisson(2.0, size=(g, n)).astype(np.float64)
     G = np.abs(rng.randn(g, k))
     C = np.abs(rng.randn(k, n))
-    slv = _solver(kernels, X, k)
+    slv = _solver(kernels, X, k, transpose_copy)
     slv._load_factors(G, C)
+    if transpose_copy:
+        np.testing.assert_array_equal(slv.XT.data[:n, :g].cpu().numpy(), X.T.astype(np.float32))
+        assert float(slv.XT.data[:, g:].abs().sum().cpu()) == 0.0
     slv._products_for_G(None)
     torch.cuda.synchronize()
-    xht = slv.R_xht.view(g, slv.kp)[:, :k].cpu().numpy()
+    xht = slv.R_xht.view(slv.kp, slv.ldg)[:k, :g].cpu().numpy().T
     cct = slv.R_cct.view(slv.kp, slv.kp)[:k, :k].cpu().numpy()
     assert rel_fro(xht, X @ C.T) < 2e-5
     assert rel_fro(cct, C @ C.T) < 1e-12
-    assert np.all(slv.R_xht.view(g, slv.kp)[:, k:].cpu().numpy() == 0)
-    kernels.gram(slv.G64, slv.kp, 1, g, k, slv.kp, slv.gram_part, slv.gtg, None)
-    kernels.wtx_partial(slv.X.data, slv.X.ldx, g, slv.X.ncols, slv.G32, slv.kp, slv.PB, slv.ldc, slv.SB, None)
-    kernels.reduce_cols(slv.PB, slv.SB, slv.kp, slv.ldc, slv.X.ncols, slv.NB, None)
+    assert np.all(slv.R_xht.view(slv.kp, slv.ldg)[k:, :g].cpu().numpy() == 0)
+    kernels.gram(slv.G64, 1, slv.ldg, g, k, slv.kp, slv.gram_part, slv.gtg, None)
+    kernels.wtx_partial(slv.X.data, slv.X.ldx, g, slv.X.ncols, slv.Gs32, slv.kp, slv.PB, slv.ldn, slv.SB, None)
+    kernels.reduce_cols(slv.PB, slv.SB, slv.kp, slv.ldn, slv.X.ncols, slv.NB, None)
     torch.cuda.synchronize()
     wtx = slv.NB[:k, :n].cpu().numpy()
     gtg = slv.gtg.view(slv.kp, slv.kp)[:k, :k].cpu().numpy()
     assert rel_fro(wtx, G.T @ X) < 2e-5
     assert rel_fro(gtg, G.T @ G) < 1e-12
     # residuals
-    kernels.residual(slv.X.data, slv.X.ldx, g, slv.X.ncols, slv.G32, slv.C32, slv.ldc, slv.kp, 1, slv.res_part,
+    kernels.residual(slv.X.data, slv.X.ldx, g, slv.X.ncols, slv.Gs32, slv.Ct32, slv.ldn, slv.kp, 1, slv.res_part,
                      slv.res_out)
     l1 = float(slv.res_out.cpu()[0])
     assert abs(l1 - np.abs(X - G @ C).sum()) / np.abs(X - G @ C).sum() < 2e-5
@@ -65,7 +69,7 @@ def test_single_update_matches_oracle(kernels, solver):
     import scrna_b200._lib as L
     torch = kernels.torch
     rng = np.random.RandomState(11)
-    rows, k, kp = 777, 7, 8
+    rows, k, kp, ld = 777, 7, 8, 800
     W = np.abs(rng.randn(rows, k))
     W[rng.rand(rows, k) < 0.25] = 0.0
     A = np.abs(rng.randn(50, k))
@@ -74,45 +78,37 @@ def test_single_update_matches_oracle(kernels, solver):
     perm = rng.permutation(k).astype(np.int32)
     l1, l2 = 7.5, 2.5
     dev = torch.device("cuda")
-    for layout in ("rows", "cols"):
-        if layout == "rows":
-            rs, cs, ld = kp, 1, kp
-            F = np.zeros((rows, kp)); F[:, :k] = W
-            N = np.zeros((rows, kp)); N[:, :k] = XHt
-        else:
-            ld = 800
-            rs, cs = 1, ld
-            F = np.zeros((kp, ld)); F[:k, :rows] = W.T
-            N = np.zeros((kp, ld)); N[:k, :rows] = XHt.T
-        F64 = torch.from_numpy(F).to(dev)
-        F32 = torch.zeros_like(F64, dtype=torch.float32)
-        num = torch.from_numpy(N).to(dev)
-        Gm = np.zeros((kp, kp)); Gm[:k, :k] = HHt
-        gram = torch.from_numpy(Gm).to(dev)
-        pp = np.zeros((1, kp), dtype=np.int32); pp[0, :k] = perm
-        perms = torch.from_numpy(pp).to(dev)
-        nblk = kernels.update_blocks(rows)
-        viol = torch.zeros(nblk, dtype=torch.float64, device=dev)
-        ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
-        code = L.SOLVER_CD if solver == "cd" else L.SOLVER_MU
-        kernels.update(code, F64, F32, rs, cs, rows, k, kp, num, gram, l1, l2, perms, 1, 0, viol, ctrl)
-        torch.cuda.synchronize()
-        out = F64.cpu().numpy()
-        got = out[:, :k] if layout == "rows" else out[:k, :rows].T
-        Wref = W.copy()
-        if solver == "cd":
-            H2 = HHt.copy(); H2.flat[:: k + 1] += l2
-            v = no.cd_sweep(Wref, H2, XHt - l1, perm)
-            assert abs(float(viol.sum().cpu()) - v) <= 1e-11 * v
-            np.testing.assert_array_equal(got == 0, Wref == 0)
-        else:
-            den = Wref @ HHt + l1 + l2 * Wref
-            den[den == 0] = no.EPSILON
-            Wref = Wref * (XHt / den)
-        np.testing.assert_allclose(got, Wref, rtol=1e-12, atol=1e-300)
-        shadow = F32.cpu().numpy()
-        shadow = shadow[:, :k] if layout == "rows" else shadow[:k, :rows].T
-        np.testing.assert_array_equal(shadow, Wref.astype(np.float32).astype(np.float32) if False else got.astype(np.float32))
+    F = np.zeros((kp, ld)); F[:k, :rows] = W.T
+    N = np.zeros((kp, ld)); N[:k, :rows] = XHt.T
+    F64 = torch.from_numpy(F).to(dev)
+    S32 = torch.full((rows, kp), -1.0, dtype=torch.float32, device=dev)
+    T32 = torch.zeros((kp, ld), dtype=torch.float32, device=dev)
+    num = torch.from_numpy(N).to(dev)
+    Gm = np.zeros((kp, kp)); Gm[:k, :k] = HHt
+    gram = torch.from_numpy(Gm).to(dev)
+    pp = np.zeros((1, kp), dtype=np.int32); pp[0, :k] = perm
+    perms = torch.from_numpy(pp).to(dev)
+    viol = torch.zeros(kernels.update_blocks(rows), dtype=torch.float64, device=dev)
+    ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
+    code = L.SOLVER_CD if solver == "cd" else L.SOLVER_MU
+    kernels.update(code, F64, ld, rows, k, kp, num, gram, l1, l2, perms, 1, 0, S32, T32, viol, ctrl)
+    torch.cuda.synchronize()
+    got = F64.cpu().numpy()[:k, :rows].T
+    Wref = W.copy()
+    if solver == "cd":
+        H2 = HHt.copy(); H2.flat[:: k + 1] += l2
+        v = no.cd_sweep(Wref, H2, XHt - l1, perm)
+        assert abs(float(viol.sum().cpu()) - v) <= 1e-11 * v
+        np.testing.assert_array_equal(got == 0, Wref == 0)
+    else:
+        den = Wref @ HHt + l1 + l2 * Wref
+        den[den == 0] = no.EPSILON
+        Wref = Wref * (XHt / den)
+    np.testing.assert_allclose(got, Wref, rtol=1e-12, atol=1e-300)
+    s32 = S32.cpu().numpy()
+    np.testing.assert_array_equal(s32[:, :k], got.astype(np.float32))
+    assert np.all(s32[:, k:] == 0)
+    np.testing.assert_array_equal(T32.cpu().numpy()[:k, :rows].T, got.astype(np.float32))
 
 
 def test_nmf_clustering_default_data_vs_reference_golden(kernels, default_sim, golden):

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--k", type=int, nargs="+", default=[8])
     ap.add_argument("--sa", type=int, nargs="*", default=[])
     ap.add_argument("--sb", type=int, nargs="*", default=[])
+    ap.add_argument("--lowmem", action="store_true")
     args = ap.parse_args()
     kn = default_kernels()
     g, n = args.genes, args.cells
@@ -59,17 +60,24 @@ def main():
         kp = slv.kp
         sa_list = args.sa or [slv.SA]
         sb_list = args.sb or [slv.SB]
-        for sa in sa_list:
-            PA = torch.empty((sa, g, kp), dtype=torch.float32, device=dev)
-            med, best = timeit(lambda: kn.xht_partial(X, ldx, g, dm.ncols, slv.C32, slv.ldc, kp, PA, sa, None))
-            out.append(dict(kernel="xht_partial", k=k, nsplit=sa, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
-            print(out[-1], flush=True)
         for sb in sb_list:
-            PB = torch.empty((sb, kp, slv.ldc), dtype=torch.float32, device=dev)
-            med, best = timeit(lambda: kn.wtx_partial(X, ldx, g, dm.ncols, slv.G32, kp, PB, slv.ldc, sb, None))
-            out.append(dict(kernel="wtx_partial", k=k, nsplit=sb, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
+            PB = torch.zeros((sb, kp, slv.ldn), dtype=torch.float32, device=dev)
+            med, best = timeit(lambda: kn.wtx_partial(X, ldx, g, dm.ncols, slv.Gs32, kp, PB, slv.ldn, sb, None))
+            out.append(dict(kernel="sweep_X(K3)", k=k, nsplit=sb, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
             print(out[-1], flush=True)
-        med, best = timeit(lambda: kn.residual(X, ldx, g, dm.ncols, slv.G32, slv.C32, slv.ldc, kp, 1, slv.res_part, slv.res_out))
+        XT = slv.XT
+        for sa in sa_list:
+            PA = torch.zeros((sa, kp, slv.ldg), dtype=torch.float32, device=dev)
+            med, best = timeit(lambda: kn.wtx_partial(XT.data, XT.ldx, XT.g, slv.gcols, slv.Cs32, kp, PA, slv.ldg, sa, None))
+            out.append(dict(kernel="sweep_XT(K1)", k=k, nsplit=sa, ms=med, best_ms=best, gbs=XT.g * XT.ldx * 4 / med / 1e6))
+            print(out[-1], flush=True)
+        if args.lowmem:
+            sa0 = kn.xht_splits(g, dm.ncols, kp)
+            PA0 = torch.zeros((sa0, g, kp), dtype=torch.float32, device=dev)
+            med, best = timeit(lambda: kn.xht_partial(X, ldx, g, dm.ncols, slv.Ct32, slv.ldn, kp, PA0, sa0, None))
+            out.append(dict(kernel="xht_partial(lowmem K1)", k=k, nsplit=sa0, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
+            print(out[-1], flush=True)
+        med, best = timeit(lambda: kn.residual(X, ldx, g, dm.ncols, slv.Gs32, slv.Ct32, slv.ldn, kp, 1, slv.res_part, slv.res_out))
         out.append(dict(kernel="residual_l1", k=k, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
         print(out[-1], flush=True)
         # whole iterations
