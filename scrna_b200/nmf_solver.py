@@ -83,7 +83,8 @@ class DeviceMatrix:
             r1 = min(g, r0 + rows_per_band)
             band = torch.from_numpy(np.ascontiguousarray(arr[r0:r1])).to(dev)
             kernels.convert_pad(band, n, out[r0:r1], ldx, r1 - r0, n)
-        torch.cuda.current_stream().synchronize()
+        if out.is_cuda:
+            torch.cuda.current_stream().synchronize()
         return cls(out, n)
 
     def transposed(self, kernels):

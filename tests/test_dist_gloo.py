@@ -1,0 +1,92 @@
+"""World-size-2 test of the multi-GPU host logic on CPU (gloo): cell sharding, all-reduce payload,
+stop rule agreement.  Compute is a test-only stand-in (tests/fake_kernels.py); the CUDA kernels
+themselves are covered by the -m gpu tests."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, case, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_kernels import FakeKernels
+        from oracle import nmf_oracle as no
+        from scrna_b200.nmf_solver import DeviceMatrix, NmfSolver, TorchDistComm, shard_bounds
+        rng = np.random.RandomState(7)
+        g, n, k = 60, 101, 4
+        mu = rng.gamma(2.0, 1.0, size=(g, 1)) * (1 + (rng.rand(g, 3) < 0.3) @ (rng.rand(3, n) < 0.4) * 3.0)
+        X = rng.poisson(mu).astype(np.float64)
+        W0, H0 = no.nndsvdar_init(X, k)
+        c0, c1 = shard_bounds(n, world, rank)
+        kn = FakeKernels()
+        dm = DeviceMatrix.from_host(X[:, c0:c1], kn, device=torch.device("cpu"))
+        slv = NmfSolver(dm, k, kernels=kn, comm=TorchDistComm())
+        solver, first = case
+        if solver == "cd":
+            if first == "G":
+                Wr, Hr, nr, _ = no.nmf_cd(X, W0, H0, 0.5, 0.5, 0.1, 0.1, tol=1e-3, max_iter=80)
+                res = slv.fit(W0, H0[:, c0:c1], solver="cd", l1_G=0.5, l2_G=0.1, l1_C=0.5, l2_C=0.1, tol=1e-3,
+                              max_iter=80, first="G", poll=3)
+                G, C = res.G, res.C
+            else:  # factorise X^T: sklearn W = C^T (updated first), H = G^T
+                Wt, Ht, nr, _ = no.nmf_cd(X.T, H0.T.copy(), W0.T.copy(), 0.5, 0.5, 0.1, 0.1, tol=1e-3, max_iter=80)
+                Wr, Hr = Ht.T, Wt.T
+                res = slv.fit(W0, H0[:, c0:c1], solver="cd", l1_G=0.5, l2_G=0.1, l1_C=0.5, l2_C=0.1, tol=1e-3,
+                              max_iter=80, first="C", poll=3)
+                G, C = res.G, res.C
+        else:
+            Wr, Hr, nr, _ = no.nmf_mu(X, W0, H0, 0.5, 0.5, 0.1, 0.1, tol=1e-4, max_iter=60)
+            res = slv.fit(W0, H0[:, c0:c1], solver="mu", l1_G=0.5, l2_G=0.1, l1_C=0.5, l2_C=0.1, tol=1e-4,
+                          max_iter=60)
+            G, C = res.G, res.C
+        ok = (res.n_iter == nr
+              and np.linalg.norm(G - Wr) / np.linalg.norm(Wr) < 1e-4
+              and np.linalg.norm(C - Hr[:, c0:c1]) / np.linalg.norm(Hr[:, c0:c1]) < 1e-4)
+        ret[rank] = (bool(ok), int(res.n_iter), int(nr))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", [("cd", "G"), ("cd", "C"), ("mu", "G")])
+def test_sharded_fit_world2(case):
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, case, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        ok, n_iter, n_ref = ret[r]
+        assert ok, (r, n_iter, n_ref)
+    assert ret[0][1] == ret[1][1]
+
+
+def test_shard_bounds_cover_and_balance():
+    from scrna_b200.nmf_solver import shard_bounds
+    for n in (1, 7, 100, 100000, 100003):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
