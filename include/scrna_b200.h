@@ -180,6 +180,68 @@ int scrna_reject_stats(const float* X, int64_t ldx, int g, int64_t ncols, const 
                        const double* H64, int64_t ldc, const int32_t* labels, double* out, int64_t ldo,
                        void* stream);
 
+/* ---- SC3 (scRNA/sc3_clustering_impl.py:106-260, scRNA/sc3_clustering.py:58-109); all fp64 ------------ */
+
+/* K9 / K19 pairwise over the COLUMNS of X (F x N row-major, leading dimension ld): out is N x N.
+ * op 0: Euclidean, sqrt(sum_f (X[f][i]-X[f][j])^2) summed in f order without FMA == scipy pdist
+ *       (sc3_clustering_impl.py:129-130; also pdist(consensus) at :252 since the consensus is symmetric);
+ * op 1: dot product Gram sum_f X[f][i]*X[f][j] (np.corrcoef at :124, spearmanr at :126). */
+int scrna_pairwise_f64(const double* X, int64_t ld, int F, int N, int op, double* out, int64_t ldo, void* stream);
+/* X[:, j] -= mean_f X[f][j] in place; mean (N doubles) is returned (np.cov centring). */
+int scrna_col_center_f64(double* X, int64_t ld, int F, int N, double* mean, void* stream);
+/* out = 1 - corrcoef from the Gram G of centred columns, numpy op order: G/(F-1), /std_i, /std_j, clip. */
+int scrna_corr_epilogue_f64(const double* G, int64_t ldg, int N, int F, double* out, int64_t ldo, void* stream);
+/* K10 average ranks (scipy.stats.rankdata 'average') of every ROW of Xt (N cells x F genes). */
+int scrna_rank_avg_f64(const double* Xt, int64_t ld, int N, int F, double* R, int64_t ldr, void* stream);
+int scrna_transpose_f64(const double* src, int64_t ld_src, int64_t rows, int64_t cols, double* dst,
+                        int64_t ld_dst, void* stream);
+
+/* K11 pca: out = (dm - colmean) with +-inf -> nan, divided by the column nanstd unless all are zero
+ * (sc3_clustering_impl.py:161-173).  sd: n doubles out; scratch: 1 int. */
+int scrna_pca_prepare_f64(const double* dm, int64_t ld, int n, double* out, int64_t ldo, double* sd,
+                          int32_t* scratch, void* stream);
+/* K12 the reference's "spectral" matrix (sc3_clustering_impl.py:143-150); work: 2n+1 doubles. */
+int scrna_laplacian_f64(const double* dm, int64_t ld, int n, double* out, int64_t ldo, double* work, void* stream);
+/* K13 one-sided Jacobi SVD of M (n x n): right singular vectors, replaces scipy.linalg.svd
+ * (sc3_clustering_impl.py:178).  init: AT = M^T, VT = I.  sweep: all column pairs once (round-robin),
+ * `rotated` += rotations applied (0 after a sweep == converged).  Singular values^2 = row norms of AT. */
+int scrna_jacobi_init_f64(const double* M, int64_t ldm, int n, double* AT, double* VT, int64_t ld, void* stream);
+int scrna_jacobi_sweep_f64(double* AT, double* VT, int64_t ld, int n, double tol, int32_t* rotated, void* stream);
+int scrna_row_sqnorm_f64(const double* AT, int64_t ld, int n, double* out, void* stream);
+/* out[i][r] = VT[order[r]][i] : the first c right singular vectors as columns. */
+int scrna_gather_vectors_f64(const double* VT, int64_t ld, int n, const int32_t* order, int c, double* out,
+                             int64_t ldo, void* stream);
+
+/* K14-K17 k-means as sklearn KMeans(init='k-means++', algorithm='lloyd') runs it
+ * (sc3_clustering_impl.py:215-217).  state: 8 doubles {tol, potential, shift_tot, inertia, changed, n_empty}. */
+int scrna_km_prepare(const double* V, int64_t ldv, int n, int d, double* X, int64_t ldx, double* xsq,
+                     double* work, double* state, void* stream);
+int scrna_kmeans_pp(const double* X, int64_t ldx, int n, int d, const double* xsq, int k, double u0,
+                    const double* uniforms, int ntrials, double* closest, double* cand_dist, double* cums,
+                    double* pots, int32_t* cand, int32_t* idx, double* state, double* C, int64_t ldc,
+                    void* stream);
+int scrna_lloyd_assign(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc, int k,
+                       int32_t* labels, void* stream);
+int scrna_lloyd_sums(const double* X, int64_t ldx, int n, int d, const int32_t* labels, int k, double* sums,
+                     int64_t lds, int32_t* counts, void* stream);
+int scrna_lloyd_finish(double* Cnew, const double* Cold, int64_t ldc, int k, int d, const int32_t* counts,
+                       const int32_t* labels, int32_t* labels_old, int n, double* state, void* stream);
+int scrna_km_cell_dist(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc,
+                       const int32_t* labels, double* out, void* stream);
+int scrna_km_inertia(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc,
+                     const int32_t* labels, double* celld, double* state, void* stream);
+int scrna_km_relocate(const double* X, int64_t ldx, int n, int d, const double* Cold, int64_t ldc, double* sums,
+                      int64_t lds, int32_t* counts, const int32_t* labels, double* celld, int k, void* stream);
+
+/* K18 co-association counts (sc3_clustering_impl.py:222-241) and consensus = M / cnt (sc3_clustering.py:105). */
+int scrna_coassoc_accum(const int32_t* labels, int n, int32_t* M, int64_t ld, void* stream);
+int scrna_consensus_scale(const int32_t* M, int64_t ldm, int n, double cnt, double* C, int64_t ldc, void* stream);
+/* K20 + K21 complete linkage (NN-chain, SciPy tie-breaking) and cut_tree(n_clusters)
+ * (sc3_clustering_impl.py:254-256).  D (n x n) is destroyed; Z: (n-1) x 4 SciPy linkage matrix out;
+ * merges: (n-1) x 3 scratch; iwork: 8n + 4(2n-1) ints. */
+int scrna_hclust_complete(double* D, int64_t ld, int n, int n_clusters, int32_t* labels, double* Z, double* merges,
+                          int32_t* iwork, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@ not need a GPU; constructing a solver does, and fails loudly otherwise.
 """
 from .abstract_clustering import AbstractClustering
 from .nmf_clustering import NmfClustering, NmfClustering_initW, NmfClustering_fixW, DaNmfClustering
+from .sc3_clustering import SC3Clustering
 
 __all__ = ["AbstractClustering", "NmfClustering", "NmfClustering_initW", "NmfClustering_fixW",
-           "DaNmfClustering"]
+           "DaNmfClustering", "SC3Clustering"]

@@ -53,6 +53,30 @@ _SIGNATURES = {
                          c_ptr, c_ptr],
     "scrna_reject_stats": [c_ptr, c_i64, c_int, c_i64, c_ptr, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_i64,
                            c_ptr],
+    # ---- SC3 ----
+    "scrna_pairwise_f64": [c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_i64, c_ptr],
+    "scrna_col_center_f64": [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr],
+    "scrna_corr_epilogue_f64": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr],
+    "scrna_rank_avg_f64": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr],
+    "scrna_transpose_f64": [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr],
+    "scrna_pca_prepare_f64": [c_ptr, c_i64, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr],
+    "scrna_laplacian_f64": [c_ptr, c_i64, c_int, c_ptr, c_i64, c_ptr, c_ptr],
+    "scrna_jacobi_init_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_i64, c_ptr],
+    "scrna_jacobi_sweep_f64": [c_ptr, c_ptr, c_i64, c_int, c_dbl, c_ptr, c_ptr],
+    "scrna_row_sqnorm_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr],
+    "scrna_gather_vectors_f64": [c_ptr, c_i64, c_int, c_ptr, c_int, c_ptr, c_i64, c_ptr],
+    "scrna_km_prepare": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
+    "scrna_kmeans_pp": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_dbl, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                        c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
+    "scrna_lloyd_assign": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_int, c_ptr, c_ptr],
+    "scrna_lloyd_sums": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_ptr, c_i64, c_ptr, c_ptr],
+    "scrna_lloyd_finish": [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr],
+    "scrna_km_cell_dist": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr],
+    "scrna_km_inertia": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
+    "scrna_km_relocate": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_int, c_ptr],
+    "scrna_coassoc_accum": [c_ptr, c_int, c_ptr, c_i64, c_ptr],
+    "scrna_consensus_scale": [c_ptr, c_i64, c_int, c_dbl, c_ptr, c_i64, c_ptr],
+    "scrna_hclust_complete": [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
 }
 
 # entry points that return a count / version instead of a status code

@@ -1,0 +1,454 @@
+// SC3 k-means ensemble for sm_100a: sklearn KMeans(n_init=10, init='k-means++', algorithm='lloyd') as the
+// reference calls it (scRNA/sc3_clustering_impl.py:206-219 -> SP/sklearn/cluster/_kmeans.py:180-279,
+// 630-758, 1436-1562; _k_means_lloyd.pyx:168-218; _k_means_common.pyx:167-300), fp64.
+//
+//   km_prepare      : X = V[:, :d] - mean, squared row norms, tol = mean(var) * 1e-4
+//   K14 kpp_*       : greedy k-means++ with the uniforms pre-drawn on the host (the reference draws them
+//                     from the global legacy RandomState)
+//   K15 lloyd_assign: labels = argmin_j (|c_j|^2 - 2 x.c_j), ties -> lowest j (one warp per cell)
+//   K16 lloyd_update: per-cluster sums in cell order (deterministic), average, shifts, change flag
+//   K17 inertia
+// The host (scrna_b200/sc3_clustering_impl.py) only sequences launches and reads three scalars per
+// Lloyd iteration for the stop rule.
+#include "common.cuh"
+
+namespace scrna {
+
+// state block of one k-means run (device, doubles): see KM_* offsets
+enum { KM_TOL = 0, KM_POT = 1, KM_SHIFT = 2, KM_INERTIA = 3, KM_CHANGED = 4, KM_EMPTY = 5, KM_STATE = 8 };
+
+// ---- prepare ---------------------------------------------------------------------------------------
+__global__ void km_colstats_kernel(const double* __restrict__ V, int64_t ldv, int n, int d,
+                                   double* __restrict__ mean, double* __restrict__ var) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= d) return;
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += V[(int64_t)i * ldv + f];
+  const double m = s / (double)n;
+  double q = 0.0;
+  for (int i = 0; i < n; ++i) { const double t = V[(int64_t)i * ldv + f] - m; q += t * t; }
+  mean[f] = m;
+  var[f] = q / (double)n;
+}
+
+__global__ void km_center_kernel(const double* __restrict__ V, int64_t ldv, int n, int d,
+                                 const double* __restrict__ mean, double* __restrict__ X, int64_t ldx,
+                                 double* __restrict__ xsq) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int f = lane; f < d; f += 32) {
+    const double v = V[(int64_t)i * ldv + f] - mean[f];
+    X[(int64_t)i * ldx + f] = v;
+    s = fma(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) xsq[i] = s;
+}
+
+__global__ void km_tol_kernel(const double* __restrict__ var, int d, double* __restrict__ state) {
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int f = 0; f < d; ++f) s += var[f];
+    state[KM_TOL] = (s / (double)d) * 1e-4;
+  }
+}
+
+// ---- k-means++ -------------------------------------------------------------------------------------
+// first centre: RandomState.choice(n, p=1/n) == searchsorted(cumsum(p)/cumsum(p)[-1], u, side='right')
+__global__ void kpp_first_kernel(int n, double u, int* __restrict__ idx) {
+  if (threadIdx.x != 0) return;
+  const double p = 1.0 / (double)n;
+  // cdf[i] = fl(cumsum)(i) / cdf[n-1]; sequential like numpy
+  double c = 0.0, last = 0.0;
+  for (int i = 0; i < n; ++i) last += p;
+  int pick = n;
+  for (int i = 0; i < n; ++i) {
+    c += p;
+    if (c / last > u) { pick = i; break; }
+  }
+  if (pick > n - 1) pick = n - 1;
+  idx[0] = pick;
+}
+
+// d2[t][i] = max(xsq[i] + xsq[c_t] - 2 x_i.x_{c_t}, 0); optionally min with closest[i]; one warp per cell
+template <int MAXT>
+__global__ void __launch_bounds__(256)
+kpp_dist_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const double* __restrict__ xsq,
+                const int* __restrict__ cand, int ntr, const double* __restrict__ closest,
+                double* __restrict__ out /* ntr x n */) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  double dot[MAXT];
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) dot[t] = 0.0;
+  const double* xi = X + (int64_t)i * ldx;
+  for (int f = lane; f < d; f += 32) {
+    const double v = xi[f];
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t)
+      if (t < ntr) dot[t] = fma(v, X[(int64_t)cand[t] * ldx + f], dot[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) dot[t] = warp_sum(dot[t]);
+  if (lane == 0) {
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t)
+      if (t < ntr) {
+        // _euclidean_distances: (-2*dot + XX) + YY, clipped at 0
+        double v = (-2.0 * dot[t] + xsq[cand[t]]) + xsq[i];
+        v = fmax(v, 0.0);
+        if (closest) v = fmin(closest[i], v);
+        out[(int64_t)t * n + i] = v;
+      }
+  }
+}
+
+// sums of each row of a (rows x n) matrix in a fixed order: one block per row
+__global__ void __launch_bounds__(1024)
+row_sums_kernel(const double* __restrict__ M, int n, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const double* row = M + (int64_t)blockIdx.x * n;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += row[i];
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+// candidates = searchsorted(cumsum(closest), u_t * pot), clipped to n-1.  Single block; the cumsum is a
+// chunked scan (per-thread sequential chunks, then offsets) kept in global scratch.
+__global__ void __launch_bounds__(1024)
+kpp_candidates_kernel(const double* __restrict__ closest, int n, const double* __restrict__ uniforms, int ntr,
+                      const double* __restrict__ state, double* __restrict__ cums, int* __restrict__ cand) {
+  __shared__ double chunk_sum[1024];
+  const int T = blockDim.x;
+  const int per = (n + T - 1) / T;
+  const int b = threadIdx.x * per, e = min(n, b + per);
+  double s = 0.0;
+  for (int i = b; i < e; ++i) s += closest[i];
+  chunk_sum[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double run = 0.0;
+    for (int t = 0; t < T; ++t) { const double v = chunk_sum[t]; chunk_sum[t] = run; run += v; }
+  }
+  __syncthreads();
+  double run = chunk_sum[threadIdx.x];
+  for (int i = b; i < e; ++i) { run += closest[i]; cums[i] = run; }
+  __syncthreads();
+  if (threadIdx.x < ntr) {
+    const double val = uniforms[threadIdx.x] * state[KM_POT];
+    int lo = 0, hi = n;  // first index with cums[idx] >= val (side='left')
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cums[mid] < val) lo = mid + 1; else hi = mid;
+    }
+    if (lo > n - 1) lo = n - 1;
+    cand[threadIdx.x] = lo;
+  }
+}
+
+// pick the candidate with the smallest potential (first minimum), adopt its distances
+__global__ void kpp_select_kernel(const double* __restrict__ pots, int ntr, const int* __restrict__ cand,
+                                  const double* __restrict__ dmin /* ntr x n */, int n,
+                                  double* __restrict__ closest, double* __restrict__ state,
+                                  int* __restrict__ idx, int c) {
+  __shared__ int best;
+  if (threadIdx.x == 0) {
+    int b = 0;
+    for (int t = 1; t < ntr; ++t)
+      if (pots[t] < pots[b]) b = t;
+    best = b;
+    state[KM_POT] = pots[b];
+    idx[c] = cand[b];
+  }
+  __syncthreads();
+  const double* src = dmin + (int64_t)best * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) closest[i] = src[i];
+}
+
+__global__ void kpp_first_pot_kernel(const double* __restrict__ pots, double* __restrict__ state) {
+  if (threadIdx.x == 0) state[KM_POT] = pots[0];
+}
+
+__global__ void gather_centers_kernel(const double* __restrict__ X, int64_t ldx, int d, const int* __restrict__ idx,
+                                      int k, double* __restrict__ C, int64_t ldc) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (f < d && j < k) C[(int64_t)j * ldc + f] = X[(int64_t)idx[j] * ldx + f];
+}
+
+// ---- Lloyd ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lloyd_assign_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const double* __restrict__ C,
+                    int64_t ldc, int k, int* __restrict__ labels) {
+  extern __shared__ double csq[];  // k squared centre norms
+  for (int j = threadIdx.x >> 5; j < k; j += (blockDim.x >> 5)) {
+    double s = 0.0;
+    for (int f = threadIdx.x & 31; f < d; f += 32) { const double v = C[(int64_t)j * ldc + f]; s = fma(v, v, s); }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) csq[j] = s;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const double* xi = X + (int64_t)i * ldx;
+  double best = 0.0;
+  int bj = 0;
+  for (int j = 0; j < k; ++j) {
+    double dot = 0.0;
+    for (int f = lane; f < d; f += 32) dot = fma(xi[f], C[(int64_t)j * ldc + f], dot);
+    dot = warp_sum(dot);
+    const double v = csq[j] - 2.0 * dot;
+    if (j == 0 || v < best) { best = v; bj = j; }
+  }
+  if (lane == 0) labels[i] = bj;
+}
+
+// sums[j][f] = sum over cells with label j, in cell order; counts[j]
+__global__ void __launch_bounds__(128)
+lloyd_sums_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const int* __restrict__ labels,
+                  double* __restrict__ sums, int64_t lds, int* __restrict__ counts) {
+  const int j = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) {
+    if (labels[i] == j) {
+      ++cnt;
+      if (f < d) s += X[(int64_t)i * ldx + f];
+    }
+  }
+  if (f < d) sums[(int64_t)j * lds + f] = s;
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[j] = cnt;
+}
+
+// averages, empty-cluster handling (copy from the heaviest cluster, _k_means_common.pyx:262-280), shifts,
+// label-change flag; single block
+__global__ void __launch_bounds__(1024)
+lloyd_finish_kernel(double* __restrict__ Cnew, const double* __restrict__ Cold, int64_t ldc, int k, int d,
+                    const int* __restrict__ counts, const int* __restrict__ labels, int* __restrict__ labels_old,
+                    int n, double* __restrict__ state) {
+  __shared__ double scratch[32];
+  __shared__ int s_changed, s_amax, s_empty;
+  if (threadIdx.x == 0) {
+    int am = 0, ne = 0;
+    for (int j = 0; j < k; ++j) { if (counts[j] > counts[am]) am = j; ne += (counts[j] == 0); }
+    s_amax = am; s_empty = ne; s_changed = 0;
+  }
+  __syncthreads();
+  for (int j = 0; j < k; ++j) {
+    if (counts[j] > 0) {
+      const double alpha = 1.0 / (double)counts[j];
+      for (int f = threadIdx.x; f < d; f += blockDim.x) Cnew[(int64_t)j * ldc + f] *= alpha;
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < k; ++j) {
+    if (counts[j] == 0)
+      for (int f = threadIdx.x; f < d; f += blockDim.x) Cnew[(int64_t)j * ldc + f] = Cnew[(int64_t)s_amax * ldc + f];
+  }
+  __syncthreads();
+  double tot = 0.0;  // sum_j shift_j^2 with shift_j = sqrt(sum_f diff^2)
+  for (int j = 0; j < k; ++j) {
+    double s = 0.0;
+    for (int f = threadIdx.x; f < d; f += blockDim.x) {
+      const double t = Cnew[(int64_t)j * ldc + f] - Cold[(int64_t)j * ldc + f];
+      s = fma(t, t, s);
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) { const double sh = sqrt(s); tot += sh * sh; }
+    __syncthreads();
+  }
+  int ch = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int l = labels[i];
+    ch |= (l != labels_old[i]);
+    labels_old[i] = l;
+  }
+  if (ch) s_changed = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    state[KM_SHIFT] = tot;
+    state[KM_CHANGED] = (double)s_changed;
+    state[KM_EMPTY] = (double)s_empty;
+  }
+}
+
+// per-cell squared distance to its assigned centre
+__global__ void __launch_bounds__(256)
+km_cell_dist_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const double* __restrict__ C,
+                    int64_t ldc, const int* __restrict__ labels, double* __restrict__ out) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const double* xi = X + (int64_t)i * ldx;
+  const double* cj = C + (int64_t)labels[i] * ldc;
+  double s = 0.0;
+  for (int f = lane; f < d; f += 32) { const double t = xi[f] - cj[f]; s = fma(t, t, s); }
+  s = warp_sum(s);
+  if (lane == 0) out[i] = s;
+}
+
+__global__ void km_store_sum_kernel(const double* __restrict__ src, double* __restrict__ state, int slot) {
+  if (threadIdx.x == 0) state[slot] = src[0];
+}
+
+// Relocate empty clusters (_k_means_common.pyx:167-212): every empty cluster (ascending id) takes the cell
+// that is farthest from its (old) centre, in descending distance order, whose contribution leaves its old
+// cluster.  Single block, launched every iteration: returns at once when no cluster is empty (the normal
+// case), otherwise computes the cell distances itself.
+__global__ void __launch_bounds__(1024)
+km_relocate_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const double* __restrict__ Cold,
+                   int64_t ldc, double* __restrict__ sums, int64_t lds, int* __restrict__ counts,
+                   const int* __restrict__ labels, double* __restrict__ celld, int k) {
+  __shared__ double bv[32];
+  __shared__ int bi[32];
+  __shared__ int s_far, s_any;
+  __shared__ double s_max;
+  if (threadIdx.x == 0) {
+    int any = 0;
+    for (int j = 0; j < k; ++j) any |= (counts[j] == 0);
+    s_any = any;
+  }
+  __syncthreads();
+  if (!s_any) return;
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = warp; i < n; i += nw) {
+      const double* xi = X + (int64_t)i * ldx;
+      const double* cj = Cold + (int64_t)labels[i] * ldc;
+      double s = 0.0;
+      for (int f = lane; f < d; f += 32) { const double t = xi[f] - cj[f]; s = fma(t, t, s); }
+      s = warp_sum(s);
+      if (lane == 0) celld[i] = s;
+    }
+  }
+  __syncthreads();
+  for (int e = 0; e < k; ++e) {
+    if (counts[e] != 0) continue;  // uniform across the block
+    double mv = -1.0; int mi = -1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (celld[i] > mv) { mv = celld[i]; mi = i; }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, mv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+      if (ov > mv || (ov == mv && oi >= 0 && (mi < 0 || oi < mi))) { mv = ov; mi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = mv; bi[threadIdx.x >> 5] = mi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double v = -1.0; int ix = -1;
+      for (int w = 0; w < (blockDim.x >> 5); ++w)
+        if (bv[w] > v || (bv[w] == v && bi[w] >= 0 && (ix < 0 || bi[w] < ix))) { v = bv[w]; ix = bi[w]; }
+      s_far = ix; s_max = v;
+    }
+    __syncthreads();
+    if (s_max <= 0.0 || s_far < 0) return;  // np.max(distances) == 0: nothing to relocate
+    const int far = s_far, old = labels[far];
+    for (int f = threadIdx.x; f < d; f += blockDim.x) {
+      const double v = X[(int64_t)far * ldx + f];
+      sums[(int64_t)old * lds + f] -= v;
+      sums[(int64_t)e * lds + f] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { counts[e] = 1; counts[old] -= 1; celld[far] = -1.0; }
+    __syncthreads();
+  }
+}
+
+}  // namespace scrna
+
+using namespace scrna;
+
+extern "C" int scrna_km_prepare(const double* V, int64_t ldv, int n, int d, double* X, int64_t ldx, double* xsq,
+                                double* work, double* state, void* stream) {
+  // work: 2*d doubles (column means, variances)
+  if (!V || !X || !xsq || !work || !state || n <= 0 || d <= 0 || ldv < d || ldx < d) return SCRNA_ERR_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  km_colstats_kernel<<<(unsigned)ceil_div(d, 64), 64, 0, st>>>(V, ldv, n, d, work, work + d);
+  km_center_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(V, ldv, n, d, work, X, ldx, xsq);
+  km_tol_kernel<<<1, 32, 0, st>>>(work + d, d, state);
+  return last_launch_status();
+}
+
+extern "C" int scrna_kmeans_pp(const double* X, int64_t ldx, int n, int d, const double* xsq, int k, double u0,
+                               const double* uniforms, int ntrials, double* closest, double* cand_dist,
+                               double* cums, double* pots, int32_t* cand, int32_t* idx, double* state, double* C,
+                               int64_t ldc, void* stream) {
+  // u0: the uniform of RandomState.choice; uniforms: (k-1)*ntrials doubles on the device (the
+  // uniform(size=ntrials) draws of centres 1..k-1); cand_dist: ntrials*n; cums: n; pots: ntrials
+  if (!X || !xsq || (!uniforms && k > 1) || !closest || !cand_dist || !cums || !pots || !cand || !idx || !state ||
+      !C || n <= 0 || d <= 0 || k <= 0 || k > n || ntrials <= 0 || ntrials > 8 || ldx < d || ldc < d)
+    return SCRNA_ERR_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  kpp_first_kernel<<<1, 32, 0, st>>>(n, u0, idx);
+  const unsigned gb = (unsigned)ceil_div(n, 8);
+  kpp_dist_kernel<8><<<gb, 256, 0, st>>>(X, ldx, n, d, xsq, idx, 1, nullptr, closest);
+  row_sums_kernel<<<1, 1024, 0, st>>>(closest, n, pots);
+  kpp_first_pot_kernel<<<1, 32, 0, st>>>(pots, state);
+  for (int c = 1; c < k; ++c) {
+    kpp_candidates_kernel<<<1, 1024, 0, st>>>(closest, n, uniforms + (int64_t)(c - 1) * ntrials, ntrials, state,
+                                             cums, cand);
+    kpp_dist_kernel<8><<<gb, 256, 0, st>>>(X, ldx, n, d, xsq, cand, ntrials, closest, cand_dist);
+    row_sums_kernel<<<ntrials, 1024, 0, st>>>(cand_dist, n, pots);
+    kpp_select_kernel<<<64, 256, 0, st>>>(pots, ntrials, cand, cand_dist, n, closest, state, idx, c);
+  }
+  dim3 grid((unsigned)ceil_div(d, 128), (unsigned)k);
+  gather_centers_kernel<<<grid, 128, 0, st>>>(X, ldx, d, idx, k, C, ldc);
+  return last_launch_status();
+}
+
+extern "C" int scrna_lloyd_assign(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc, int k,
+                                  int32_t* labels, void* stream) {
+  if (!X || !C || !labels || n <= 0 || d <= 0 || k <= 0 || ldx < d || ldc < d) return SCRNA_ERR_BADARG;
+  lloyd_assign_kernel<<<(unsigned)ceil_div(n, 8), 256, (size_t)k * sizeof(double), (cudaStream_t)stream>>>(
+      X, ldx, n, d, C, ldc, k, labels);
+  return last_launch_status();
+}
+
+extern "C" int scrna_lloyd_sums(const double* X, int64_t ldx, int n, int d, const int32_t* labels, int k,
+                                double* sums, int64_t lds, int32_t* counts, void* stream) {
+  if (!X || !labels || !sums || !counts || n <= 0 || d <= 0 || k <= 0 || ldx < d || lds < d) return SCRNA_ERR_BADARG;
+  dim3 grid((unsigned)ceil_div(d, 128), (unsigned)k);
+  lloyd_sums_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(X, ldx, n, d, labels, sums, lds, counts);
+  return last_launch_status();
+}
+
+extern "C" int scrna_lloyd_finish(double* Cnew, const double* Cold, int64_t ldc, int k, int d, const int32_t* counts,
+                                  const int32_t* labels, int32_t* labels_old, int n, double* state, void* stream) {
+  if (!Cnew || !Cold || !counts || !labels || !labels_old || !state || k <= 0 || d <= 0 || n <= 0 || ldc < d)
+    return SCRNA_ERR_BADARG;
+  lloyd_finish_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(Cnew, Cold, ldc, k, d, counts, labels, labels_old, n, state);
+  return last_launch_status();
+}
+
+extern "C" int scrna_km_cell_dist(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc,
+                                  const int32_t* labels, double* out, void* stream) {
+  if (!X || !C || !labels || !out || n <= 0 || d <= 0 || ldx < d || ldc < d) return SCRNA_ERR_BADARG;
+  km_cell_dist_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(X, ldx, n, d, C, ldc, labels, out);
+  return last_launch_status();
+}
+
+extern "C" int scrna_km_inertia(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc,
+                                const int32_t* labels, double* celld, double* state, void* stream) {
+  if (!X || !C || !labels || !celld || !state || n <= 0 || d <= 0 || ldx < d || ldc < d) return SCRNA_ERR_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  km_cell_dist_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(X, ldx, n, d, C, ldc, labels, celld);
+  row_sums_kernel<<<1, 1024, 0, st>>>(celld, n, state + KM_INERTIA);
+  return last_launch_status();
+}
+
+extern "C" int scrna_km_relocate(const double* X, int64_t ldx, int n, int d, const double* Cold, int64_t ldc,
+                                 double* sums, int64_t lds, int32_t* counts, const int32_t* labels, double* celld,
+                                 int k, void* stream) {
+  if (!X || !Cold || !sums || !counts || !labels || !celld || n <= 0 || d <= 0 || k <= 0 || ldx < d || lds < d ||
+      ldc < d)
+    return SCRNA_ERR_BADARG;
+  km_relocate_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(X, ldx, n, d, Cold, ldc, sums, lds, counts, labels, celld,
+                                                          k);
+  return last_launch_status();
+}

@@ -1,0 +1,100 @@
+"""SC3Clustering with the reference's plug-in API (scRNA/sc3_clustering.py:8-110).
+
+The five registration methods take plain callables exactly like the reference; wiring them to
+`scrna_b200.sc3_clustering_impl` (as scRNA/cmd_target.py:228-242 does with functools.partial) runs every
+stage on the GPU.  `apply()` follows the reference's loop order, RNG consumption (np.random.permutation for
+the dimension sub-sample, sc3_clustering.py:85) and consensus_mode semantics.  When the registered consensus
+builder is this package's own, the co-association counts are accumulated on the device as integers and the
+n x n matrix is formed once (identical values: the reference sums exact 0/1 matrices in fp64).
+"""
+import numpy as np
+
+from .abstract_clustering import AbstractClustering
+from . import sc3_clustering_impl as _impl
+
+
+class SC3Clustering(AbstractClustering):
+    dists_list = None
+    dimred_list = None
+    intermediate_clustering_list = None
+    build_consensus_matrix = None
+    consensus_clustering = None
+    dists = None
+    pc_range = None
+    sub_sample = None
+    consensus_mode = None
+
+    def __init__(self, data, gene_ids=None, pc_range=[4, 10], sub_sample=True, consensus_mode=0):
+        super(SC3Clustering, self).__init__(data, gene_ids=gene_ids)
+        self.dists_list = []
+        self.dimred_list = []
+        self.intermediate_clustering_list = []
+        self.consensus_clustering = lambda X: np.zeros(X.shape[0])
+        self.pc_range = pc_range
+        self.sub_sample = sub_sample
+        self.consensus_mode = consensus_mode
+
+    def set_consensus_clustering(self, consensus_clustering):
+        self.consensus_clustering = consensus_clustering
+
+    def set_build_consensus_matrix(self, build_consensus_matrix):
+        self.build_consensus_matrix = build_consensus_matrix
+
+    def add_distance_calculation(self, dist_calculation):
+        self.dists_list.append(dist_calculation)
+
+    def add_dimred_calculation(self, dimred_computation):
+        self.dimred_list.append(dimred_computation)
+
+    def add_intermediate_clustering(self, intermediate_clustering):
+        self.intermediate_clustering_list.append(intermediate_clustering)
+
+    def _uses_device_consensus(self):
+        f = self.build_consensus_matrix
+        f = getattr(f, "func", f)
+        return f is _impl.build_consensus_matrix and self.consensus_mode == 0
+
+    def apply(self):
+        assert self.pc_range[0] > 0
+        assert self.pc_range[1] < self.num_cells
+        X = self.pre_processing()
+
+        dists = [d(X, self.gene_ids[self.remain_gene_inds]) for d in self.dists_list]
+        transf = []
+        for d in dists:
+            for t in self.dimred_list:
+                transf.append(t(d))
+
+        range_inds = list(range(self.pc_range[0], self.pc_range[1] + 1))
+        if self.sub_sample and len(range_inds) > 15:
+            range_inds = np.random.permutation(range_inds)[:15]
+
+        n = self.remain_cell_inds.size
+        cnt = 0.
+        device_acc = self._uses_device_consensus()
+        if device_acc:
+            ops = _impl._ops()
+            M = ops.coassoc_new(n)
+        else:
+            consensus2 = np.zeros((n, n))
+        for cluster in self.intermediate_clustering_list:
+            for t in range(len(transf)):
+                _, deigv = transf[t]
+                labels = []
+                for d in range_inds:
+                    labels.append(cluster(deigv[:, 0:d].reshape((deigv.shape[0], d))))
+                    if self.consensus_mode == 0:
+                        if device_acc:
+                            ops.coassoc_add(M, np.array(labels[-1]))
+                        else:
+                            consensus2 += self.build_consensus_matrix(np.array(labels[-1]))
+                        cnt += 1.
+                if self.consensus_mode == 1:
+                    consensus2 += self.build_consensus_matrix(np.array(labels))
+                    cnt += 1.
+        if device_acc:
+            C = ops.consensus_from_counts(M, cnt)
+            consensus2 = _impl._remember(C.cpu().numpy(), C)
+        else:
+            consensus2 /= cnt
+        self.cluster_labels, self.dists = self.consensus_clustering(consensus2)

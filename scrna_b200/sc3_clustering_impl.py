@@ -34,3 +34,113 @@ def data_transformation_log2(data):
 
 def no_data_transformation(data):
     return data
+
+
+# --------------------------------------------------------------------------------------------------
+# Device stages.  Same signatures and NumPy-in / NumPy-out contract as the reference callables
+# (SC3Clustering's plug-in API, scRNA/sc3_clustering.py:34-56).  A result also stays resident on the
+# device, keyed by the identity of the returned array, so the next stage does not upload it again.
+# --------------------------------------------------------------------------------------------------
+import weakref
+
+_resident = {}
+
+
+def _remember(host_array, device_tensor):
+    key = id(host_array)
+    _resident[key] = (weakref.ref(host_array, lambda _r, k=key: _resident.pop(k, None)), device_tensor)
+    return host_array
+
+
+def _lookup(host_array):
+    """Device twin of `host_array`, or of the array it is a leading-columns view of, else None."""
+    hit = _resident.get(id(host_array))
+    if hit is not None and hit[0]() is host_array:
+        return hit[1]
+    base = getattr(host_array, "base", None)
+    if base is not None:
+        hit = _resident.get(id(base))
+        if hit is not None and hit[0]() is base and host_array.ndim == 2 and base.ndim == 2 \
+                and host_array.shape[0] == base.shape[0] and host_array.strides == base.strides \
+                and host_array.__array_interface__['data'][0] == base.__array_interface__['data'][0]:
+            return hit[1][:, : host_array.shape[1]]
+    return None
+
+
+def _ops():
+    from .sc3_device import default_ops
+    return default_ops()
+
+
+def distances(data, gene_ids, metric='euclidean'):
+    """cells x cells distance matrix of a transcripts x cells matrix (scRNA/sc3_clustering_impl.py:106-132):
+    'euclidean' (bit-identical to scipy pdist), 'pearson' (1 - corrcoef), 'spearman' (1 - rank corrcoef)."""
+    ops = _ops()
+    D = ops.distances(np.asarray(data, dtype=np.float64), metric)
+    return _remember(D.cpu().numpy(), D)
+
+
+def transformations(dm, components=5, method='pca'):
+    """(cells x cells matrix rebuilt from the kept components, cells x components right singular vectors)
+    of the PCA-scaled or 'spectral' distance matrix (scRNA/sc3_clustering_impl.py:135-203).  The first return
+    value is what the reference computes and its only caller discards (sc3_clustering.py:77,95)."""
+    ops = _ops()
+    dev = _lookup(dm)
+    D = dev if dev is not None else ops.to_device(np.asarray(dm, dtype=np.float64))
+    num_cells = D.shape[0]
+    M = ops.transform_matrix(D, method)
+    V, vals = ops.right_singular_vectors(M, components)
+    vecs = V.cpu().numpy()
+    vals = vals / np.sqrt(np.max((1, num_cells - 1)))
+    rebuilt = vecs.dot(np.diag(vals[:components]).dot(vecs.T))
+    return rebuilt, _remember(vecs, V)
+
+
+def kmeans_draws(k, n_init=10):
+    """The uniforms one KMeans(n_init).fit consumes from the global legacy NumPy RNG, drawn here in the
+    reference's order so that seeded runs match it."""
+    from .sc3_device import kmeans_draw_count
+    per, _ = kmeans_draw_count(k)
+    return np.random.random_sample(n_init * per)
+
+
+def intermediate_kmeans_clustering(X, k=5, n_init=10, max_iter=10000, init='k-means++'):
+    """cells x 1 labels of KMeans(n_clusters=k, n_init, max_iter, init='k-means++') on the cells x d matrix
+    (scRNA/sc3_clustering_impl.py:206-219)."""
+    if init != 'k-means++':
+        raise NotImplementedError("only init='k-means++' (the reference's default and only use) is on the device")
+    ops = _ops()
+    X = np.asarray(X)
+    n, d = X.shape
+    dev = _lookup(X)
+    V = dev if dev is not None else ops.to_device(np.ascontiguousarray(X, dtype=np.float64))
+    draws = kmeans_draws(k, n_init)
+    # V may be a column-slice view of the resident vectors: its row stride is the leading dimension
+    labels = ops.kmeans(V, d, k, draws, n_init=n_init, max_iter=max_iter)
+    assert labels.size == n
+    return labels
+
+
+def build_consensus_matrix(X):
+    """cells x cells co-association matrix of an (n_labelings x cells) label matrix, averaged over the
+    labelings (scRNA/sc3_clustering_impl.py:222-241)."""
+    ops = _ops()
+    X = np.asarray(X)
+    if X.ndim == 1:
+        X = X[np.newaxis, :]
+    n, cells = X.shape
+    M = ops.coassoc_new(cells)
+    for i in range(n):
+        ops.coassoc_add(M, X[i])
+    C = ops.consensus_from_counts(M, float(n))
+    return _remember(C.cpu().numpy(), C)
+
+
+def consensus_clustering(consensus, n_components=5):
+    """(labels, cells x cells Euclidean distances between consensus rows): pdist -> complete linkage ->
+    cut_tree(n_components) (scRNA/sc3_clustering_impl.py:244-260)."""
+    ops = _ops()
+    dev = _lookup(consensus)
+    C = dev if dev is not None else ops.to_device(np.asarray(consensus, dtype=np.float64))
+    labels, D, _ = ops.consensus_clustering(C, n_components)
+    return labels, D.cpu().numpy()

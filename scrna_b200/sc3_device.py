@@ -1,0 +1,241 @@
+"""Device-side SC3 stages (fp64) sequenced from the host: distances, transformations, k-means ensemble,
+consensus matrix and complete-linkage consensus clustering (kernels K9-K21).
+
+Every array operation is a C-ABI kernel (include/scrna_b200.h); the host sequences launches, reads a
+few scalars per k-means iteration / Jacobi sweep for the stop rules, and draws nothing: random inputs
+(k-means++ uniforms) are passed in, pre-drawn from the reference's RNG stream.
+"""
+import numpy as np
+
+from . import _lib
+
+
+def kmeans_draw_count(k):
+    """Uniform doubles one k-means++ init consumes from the legacy RandomState: choice(n, p) = 1, then
+    (k-1) x uniform(size=2+int(log k))  (SP/sklearn/cluster/_kmeans.py:231,249)."""
+    trials = 2 + int(np.log(k))
+    return 1 + (k - 1) * trials, trials
+
+
+def same_clustering(l1, l2, k):
+    """sklearn _is_same_clustering (_k_means_common.pyx:314-328)."""
+    mapping = np.full(k, -1, dtype=np.int64)
+    for a, b in zip(l1.tolist(), l2.tolist()):
+        if mapping[a] == -1:
+            mapping[a] = b
+        elif mapping[a] != b:
+            return False
+    return True
+
+
+class Sc3Ops:
+    def __init__(self, kernels=None):
+        if kernels is None:
+            from .kernels import default_kernels
+            kernels = default_kernels()
+        self.kn = kernels
+        self.torch = kernels.torch
+        self.dev = self.torch.device("cuda", self.torch.cuda.current_device())
+
+    # ---- plumbing ---------------------------------------------------------------------------------
+    def _s(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def _call(self, name, *args, launches=1):
+        self.kn.launches += launches
+        return _lib.call(name, *args)
+
+    def to_device(self, a):
+        t = self.torch
+        if isinstance(a, t.Tensor):
+            return a
+        return t.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.dev)
+
+    def empty(self, *shape, dtype=None):
+        t = self.torch
+        return t.empty(shape, dtype=dtype or t.float64, device=self.dev)
+
+    def zeros(self, *shape, dtype=None):
+        t = self.torch
+        return t.zeros(shape, dtype=dtype or t.float64, device=self.dev)
+
+    # ---- a12 distances ------------------------------------------------------------------------------
+    def distances(self, X, metric="euclidean"):
+        """X: genes x cells (numpy or device fp64) -> device n x n distance matrix."""
+        Xd = self.to_device(X)
+        F, N = Xd.shape
+        out = self.empty(N, N)
+        if metric == "euclidean":
+            self._call("scrna_pairwise_f64", Xd, N, F, N, 0, out, N, self._s())
+            return out
+        if metric == "pearson":
+            work = Xd.clone()
+        elif metric == "spearman":
+            Xt = self.empty(N, F)
+            self._call("scrna_transpose_f64", Xd, N, F, N, Xt, F, self._s())
+            Rt = self.empty(N, F)
+            self._call("scrna_rank_avg_f64", Xt, F, N, F, Rt, F, self._s())
+            work = self.empty(F, N)
+            self._call("scrna_transpose_f64", Rt, F, N, F, work, N, self._s())
+        else:
+            raise ValueError("metric must be 'euclidean', 'pearson' or 'spearman' (got %r)" % (metric,))
+        mean = self.empty(N)
+        self._call("scrna_col_center_f64", work, N, F, N, mean, self._s(), launches=2)
+        G = self.empty(N, N)
+        self._call("scrna_pairwise_f64", work, N, F, N, 1, G, N, self._s())
+        self._call("scrna_corr_epilogue_f64", G, N, N, F, out, N, self._s())
+        return out
+
+    # ---- a13 transformations ------------------------------------------------------------------------
+    def transform_matrix(self, D, method="pca"):
+        D = self.to_device(D)
+        n = D.shape[0]
+        out = self.empty(n, n)
+        if method == "spectral":
+            work = self.empty(2 * n + 1)
+            self._call("scrna_laplacian_f64", D, n, n, out, n, work, self._s(), launches=3)
+        else:
+            sd = self.empty(n)
+            scratch = self.zeros(1, dtype=self.torch.int32)
+            self._call("scrna_pca_prepare_f64", D, n, n, out, n, sd, scratch, self._s(), launches=3)
+            if int(scratch.cpu()[0]) == 0:
+                print("All values are Zero!")
+        return out
+
+    def right_singular_vectors(self, M, components, max_sweeps=40, tol=1e-15):
+        """First `components` right singular vectors of the n x n device matrix M (descending singular
+        values) by one-sided Jacobi; returns (V device n x components, singular values numpy n)."""
+        t = self.torch
+        n = M.shape[0]
+        AT = self.empty(n, n)
+        VT = self.empty(n, n)
+        self._call("scrna_jacobi_init_f64", M, n, n, AT, VT, n, self._s(), launches=2)
+        rotated = self.zeros(1, dtype=t.int32)
+        self.jacobi_sweeps = 0
+        if n > 1:
+            for _ in range(max_sweeps):
+                rotated.zero_()
+                self._call("scrna_jacobi_sweep_f64", AT, VT, n, n, float(tol), rotated, self._s(),
+                           launches=((n + 1) // 2 * 2) - 1)
+                self.jacobi_sweeps += 1
+                if int(rotated.cpu()[0]) == 0:
+                    break
+        sq = self.empty(n)
+        self._call("scrna_row_sqnorm_f64", AT, n, n, sq, self._s())
+        vals = np.sqrt(np.maximum(sq.cpu().numpy(), 0.0))
+        order = np.argsort(-vals, kind="stable").astype(np.int32)
+        c = int(components)
+        od = t.from_numpy(order[:c].copy()).to(self.dev)
+        V = self.empty(n, c)
+        self._call("scrna_gather_vectors_f64", VT, n, n, od, c, V, c, self._s())
+        return V, vals[order]
+
+    # ---- a14 k-means ----------------------------------------------------------------------------------
+    def kmeans(self, V, d, k, draws, n_init=10, max_iter=10000):
+        """KMeans(n_clusters=k, n_init, max_iter, init='k-means++').fit_predict(V[:, :d]); `draws` are the
+        n_init * kmeans_draw_count(k) uniforms of the reference's RNG stream.  Returns int32 device labels."""
+        t = self.torch
+        V = self.to_device(V)
+        n, ldv = V.shape[0], V.stride(0)
+        if V.stride(1) != 1 or ldv < d:
+            V = V.contiguous()
+            ldv = V.stride(0)
+        per, trials = kmeans_draw_count(k)
+        draws = np.ascontiguousarray(draws, dtype=np.float64)
+        if draws.size < n_init * per:
+            raise ValueError("need %d uniforms, got %d" % (n_init * per, draws.size))
+        i32 = t.int32
+        X = self.empty(n, d)
+        xsq = self.empty(n)
+        work = self.empty(2 * d)
+        state = self.zeros(8)
+        self._call("scrna_km_prepare", V, ldv, n, d, X, d, xsq, work, state, self._s(), launches=3)
+        tol = float(state.cpu()[0])
+        U = t.from_numpy(draws).to(self.dev)
+        closest = self.empty(n)
+        cand_dist = self.empty(trials * n)
+        cums = self.empty(n)
+        pots = self.empty(8)
+        cand = self.zeros(8, dtype=i32)
+        idx = self.zeros(k, dtype=i32)
+        Ca = self.empty(k, d)
+        Cb = self.empty(k, d)
+        labels = self.zeros(n, dtype=i32)
+        labels_old = self.zeros(n, dtype=i32)
+        counts = self.zeros(k, dtype=i32)
+        celld = self.empty(n)
+        best = None
+        esz = 8
+        for r in range(n_init):
+            u0 = float(draws[r * per])
+            uptr = U.data_ptr() + (r * per + 1) * esz
+            self._call("scrna_kmeans_pp", X, d, n, d, xsq, k, u0, uptr if k > 1 else None, trials, closest,
+                       cand_dist, cums, pots, cand, idx, state, Ca, d, self._s(), launches=4 * k + 1)
+            labels_old.fill_(-1)
+            cur, nxt = Ca, Cb
+            strict = False
+            for _ in range(max_iter):
+                self._call("scrna_lloyd_assign", X, d, n, d, cur, d, k, labels, self._s())
+                self._call("scrna_lloyd_sums", X, d, n, d, labels, k, nxt, d, counts, self._s())
+                self._call("scrna_km_relocate", X, d, n, d, cur, d, nxt, d, counts, labels, celld, k, self._s())
+                self._call("scrna_lloyd_finish", nxt, cur, d, k, d, counts, labels, labels_old, n, state, self._s())
+                st = state.cpu().numpy()
+                cur, nxt = nxt, cur
+                if st[4] == 0.0:
+                    strict = True
+                    break
+                if st[2] <= tol:
+                    break
+            if not strict:
+                self._call("scrna_lloyd_assign", X, d, n, d, cur, d, k, labels, self._s())
+            self._call("scrna_km_inertia", X, d, n, d, cur, d, labels, celld, state, self._s(), launches=2)
+            inertia = float(state.cpu()[3])
+            lab_host = labels.cpu().numpy()
+            if best is None or (inertia < best[1] and not same_clustering(lab_host, best[0], k)):
+                best = (lab_host.copy(), inertia)
+        return best[0]
+
+    # ---- a15 / a17 consensus --------------------------------------------------------------------------
+    def coassoc_new(self, n):
+        return self.zeros(n, n, dtype=self.torch.int32)
+
+    def coassoc_add(self, M, labels):
+        t = self.torch
+        n = M.shape[0]
+        if not isinstance(labels, t.Tensor):
+            labels = t.from_numpy(np.ascontiguousarray(labels, dtype=np.int32)).to(self.dev)
+        self._call("scrna_coassoc_accum", labels, n, M, n, self._s())
+
+    def consensus_from_counts(self, M, cnt):
+        n = M.shape[0]
+        C = self.empty(n, n)
+        self._call("scrna_consensus_scale", M, n, n, float(cnt), C, n, self._s())
+        return C
+
+    def consensus_clustering(self, C, n_clusters):
+        """pdist(C) -> complete linkage -> cut_tree(n_clusters).  Returns (labels numpy int64, device n x n
+        row-distance matrix, linkage matrix Z numpy (n-1) x 4)."""
+        t = self.torch
+        C = self.to_device(C)
+        n = C.shape[0]
+        D = self.empty(n, n)
+        self._call("scrna_pairwise_f64", C, n, n, n, 0, D, n, self._s())
+        Dwork = D.clone()
+        labels = self.zeros(n, dtype=t.int32)
+        Z = self.zeros(max(n - 1, 1), 4)
+        merges = self.zeros(max(n - 1, 1), 3)
+        iwork = self.zeros(8 * n + 4 * (2 * n - 1), dtype=t.int32)
+        if n >= 2:
+            self._call("scrna_hclust_complete", Dwork, n, n, int(n_clusters), labels, Z, merges, iwork, self._s(),
+                       launches=5)
+        return labels.cpu().numpy().astype(np.int64), D, Z.cpu().numpy()
+
+
+_ops = None
+
+
+def default_ops():
+    global _ops
+    if _ops is None:
+        _ops = Sc3Ops()
+    return _ops

@@ -120,6 +120,43 @@ def main():
         t2_W=t2.dictionary, t2_H=t2.data_matrix, t2_labels=t2.cluster_labels,
         t3_randn=draw2, t3_gene_ids=t3.gene_ids, t3_W=t3.intermediate_model[0], t3_H=t3.intermediate_model[1],
         t3_H2=t3.intermediate_model[2], t3_mixed=mixed3, t3_new=new3, t3_trg=trg3, t3_labels=t3.cluster_labels)
+    # ---- SC3 on the mixed default target data (cmd_target.py:220-242 wiring) ----------------------
+    n = mixed.shape[1]
+    k = 7
+    pc = [max(1, int(np.floor(0.04 * n))), int(np.ceil(0.07 * n))]
+    out = {"pc_range": np.array(pc), "k": np.int64(k), "seed": np.int64(3)}
+    for m in ("euclidean", "pearson", "spearman"):
+        out["D_" + m] = sc.distances(mixed.copy(), np.arange(1000), metric=m)
+        for t in ("pca", "spectral"):
+            _, vecs = sc.transformations(out["D_" + m].copy(), components=pc[1], method=t)
+            out["V_%s_%s" % (m, t)] = vecs
+
+    def run_sc3(dists, transfs, seed):
+        labs = []
+
+        def km(X, k):
+            lab = sc.intermediate_kmeans_clustering(X, k=k)
+            labs.append(np.asarray(lab).copy())
+            return lab
+        np.random.seed(seed)
+        s3 = ref.sc3_clustering.SC3Clustering(mixed, np.arange(1000), pc_range=pc, sub_sample=True,
+                                              consensus_mode=0)
+        for d in dists:
+            s3.add_distance_calculation(partial(sc.distances, metric=d))
+        for t in transfs:
+            s3.add_dimred_calculation(partial(sc.transformations, components=pc[1], method=t))
+        s3.add_intermediate_clustering(partial(km, k=k))
+        s3.set_build_consensus_matrix(sc.build_consensus_matrix)
+        s3.set_consensus_clustering(partial(sc.consensus_clustering, n_components=k))
+        s3.apply()
+        return s3.cluster_labels, np.array(labs), s3.dists
+
+    l1, km1, cd1 = run_sc3(["euclidean"], ["pca"], 3)
+    l2, km2, cd2 = run_sc3(["euclidean", "pearson", "spearman"], ["pca", "spectral"], 3)
+    out.update(labels_euclid_pca=l1, kmeans_euclid_pca=km1, cdists_euclid_pca=cd1,
+               labels_all=l2, kmeans_all=km2, cdists_all=cd2)
+    np.savez_compressed(os.path.join(HERE, "sc3.npz"), **out)
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

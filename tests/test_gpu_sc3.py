@@ -1,0 +1,186 @@
+"""Parity of the CUDA SC3 path (K9-K21, through the C ABI) against the oracle and the reference goldens.
+Bar: Euclidean distances and consensus row distances bit-exact; correlation distances 1e-12; singular vectors
+1e-8 up to sign; k-means labelings, consensus matrix and final labels identical."""
+from functools import partial
+
+import numpy as np
+import pytest
+
+from oracle import sc3_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(kernels):
+    from scrna_b200.sc3_device import Sc3Ops
+    return Sc3Ops(kernels)
+
+
+@pytest.fixture(scope="module")
+def sc3g(golden):
+    return golden("sc3")
+
+
+@pytest.fixture(scope="module")
+def mixed(golden):
+    return golden("transfer")["mixed"]
+
+
+def test_euclidean_bit_exact(ops, mixed, sc3g):
+    D = ops.distances(mixed, "euclidean").cpu().numpy()
+    np.testing.assert_array_equal(D, sc3g["D_euclidean"])
+
+
+@pytest.mark.parametrize("g,n", [(37, 5), (64, 64), (130, 129), (1000, 257), (3, 70)])
+def test_euclidean_bit_exact_shapes(ops, g, n):
+    rng = np.random.RandomState(g + n)
+    X = rng.gamma(2.0, 3.0, size=(g, n)) * (rng.rand(g, n) < 0.7)
+    np.testing.assert_array_equal(ops.distances(X, "euclidean").cpu().numpy(), so.distances(X, "euclidean"))
+
+
+def test_pearson_spearman(ops, mixed, sc3g):
+    P = ops.distances(mixed, "pearson").cpu().numpy()
+    S = ops.distances(mixed, "spearman").cpu().numpy()
+    np.testing.assert_allclose(P, sc3g["D_pearson"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(S, sc3g["D_spearman"], rtol=0, atol=1e-12)
+
+
+def test_rank_average_with_ties(ops):
+    rng = np.random.RandomState(1)
+    X = rng.randint(0, 6, size=(300, 40)).astype(np.float64)       # many ties
+    S = ops.distances(X, "spearman").cpu().numpy()
+    np.testing.assert_allclose(S, so.distances(X, "spearman"), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "pearson", "spearman"])
+@pytest.mark.parametrize("method", ["pca", "spectral"])
+def test_transformations_vs_reference(ops, sc3g, metric, method):
+    from scrna_b200 import sc3_clustering_impl as sc
+    c = int(sc3g["pc_range"][1])
+    D = sc3g["D_" + metric]
+    M = ops.transform_matrix(D, method).cpu().numpy()
+    Mref = so.laplacian_quirk(D) if method == "spectral" else so.pca_prepare(D)
+    np.testing.assert_allclose(M, Mref, rtol=1e-12, atol=1e-13)
+    rebuilt, V = sc.transformations(D, components=c, method=method)
+    ref = sc3g["V_%s_%s" % (metric, method)]
+    sgn = np.sign((V * ref).sum(axis=0))
+    np.testing.assert_allclose(V * sgn, ref, rtol=0, atol=1e-8)
+    assert rebuilt.shape == D.shape
+    assert ops.jacobi_sweeps < 30
+
+
+def test_jacobi_on_random_matrices(ops):
+    import scipy.linalg as sl
+    for n in (2, 7, 64, 151):
+        rng = np.random.RandomState(n)
+        M = rng.randn(n, n)
+        V, vals = ops.right_singular_vectors(ops.to_device(M), n)
+        _, s, vt = sl.svd(M)
+        np.testing.assert_allclose(vals, s, rtol=1e-10, atol=1e-12)
+        V = V.cpu().numpy()
+        sgn = np.sign((V * vt.T).sum(axis=0))
+        np.testing.assert_allclose(V * sgn, vt.T, rtol=0, atol=1e-8)
+
+
+def test_kmeans_labelings_vs_reference(ops, sc3g):
+    k, pc = int(sc3g["k"]), [int(v) for v in sc3g["pc_range"]]
+    V = sc3g["V_euclidean_pca"]
+    np.random.seed(int(sc3g["seed"]))
+    per, _ = so.kmeans_draw_count(k)
+    for i, d in enumerate(range(pc[0], pc[1] + 1)):
+        draws = np.random.random_sample(10 * per)
+        lab = ops.kmeans(ops.to_device(V), d, k, draws)
+        np.testing.assert_array_equal(lab, sc3g["kmeans_euclid_pca"][i])
+
+
+@pytest.mark.parametrize("n,d,k", [(200, 3, 4), (513, 17, 6), (64, 40, 2), (1000, 9, 8)])
+def test_kmeans_vs_sklearn_seeded(ops, n, d, k):
+    from sklearn.cluster import KMeans
+    rng = np.random.RandomState(n + d)
+    X = np.concatenate([rng.randn(n // k + 1, d) + 5 * rng.randn(1, d) for _ in range(k)])[:n]
+    np.random.seed(n)
+    ref = KMeans(n_clusters=k, n_init=10, max_iter=10000, init='k-means++').fit_predict(X)
+    np.random.seed(n)
+    per, _ = so.kmeans_draw_count(k)
+    got = ops.kmeans(ops.to_device(X), d, k, np.random.random_sample(10 * per))
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_kmeans_duplicate_points_empty_cluster(ops):
+    """Duplicate points force empty clusters: the relocation path must run and produce a valid labeling."""
+    X = np.repeat(np.array([[0.0, 0.0], [1.0, 1.0], [5.0, 5.0]]), 10, axis=0)
+    per, _ = so.kmeans_draw_count(5)
+    lab = ops.kmeans(ops.to_device(X), 2, 5, np.random.RandomState(0).random_sample(10 * per))
+    assert lab.shape == (30,) and lab.min() >= 0 and lab.max() < 5
+    for blk in range(3):   # identical points share a label unless a relocation split one off
+        assert len(set(lab[blk * 10:(blk + 1) * 10].tolist())) <= 3
+
+
+def test_consensus_matrix_and_clustering_vs_reference(ops, sc3g):
+    from scrna_b200 import sc3_clustering_impl as sc
+    labs = sc3g["kmeans_all"]
+    C = sc.build_consensus_matrix(labs)
+    np.testing.assert_array_equal(C, so.build_consensus_matrix(labs))
+    labels, cd = sc.consensus_clustering(C, n_components=int(sc3g["k"]))
+    np.testing.assert_array_equal(cd, sc3g["cdists_all"])
+    np.testing.assert_array_equal(labels, sc3g["labels_all"])
+
+
+@pytest.mark.parametrize("n,r,c,k", [(40, 6, 4, 3), (129, 3, 5, 7), (300, 12, 6, 5), (17, 1, 3, 2), (64, 2, 2, 64),
+                                     (50, 4, 3, 1)])
+def test_hclust_tie_heavy_vs_scipy(ops, n, r, c, k):
+    """Consensus matrices are multiples of 1/r: ties everywhere.  Linkage distances and cut labels must
+    equal SciPy's."""
+    rng = np.random.RandomState(n * 7 + r)
+    lab = rng.randint(0, c, size=(r, n))
+    cons = so.build_consensus_matrix(lab)
+    ref_labels, ref_sq, Z = so.consensus_clustering(cons, k)
+    labels, D, Zg = ops.consensus_clustering(cons, k)
+    np.testing.assert_array_equal(D.cpu().numpy(), ref_sq)
+    np.testing.assert_array_equal(Zg[:, 2], Z[:, 2])
+    np.testing.assert_array_equal(Zg[:, 3], Z[:, 3])
+    np.testing.assert_array_equal(labels, ref_labels)
+
+
+def _run_sc3(mixed, dists, transfs, k, pc, seed):
+    from scrna_b200 import SC3Clustering
+    from scrna_b200 import sc3_clustering_impl as sc
+    np.random.seed(seed)
+    s3 = SC3Clustering(mixed, np.arange(mixed.shape[0]), pc_range=pc, sub_sample=True, consensus_mode=0)
+    for d in dists:
+        s3.add_distance_calculation(partial(sc.distances, metric=d))
+    for t in transfs:
+        s3.add_dimred_calculation(partial(sc.transformations, components=pc[1], method=t))
+    s3.add_intermediate_clustering(partial(sc.intermediate_kmeans_clustering, k=k))
+    s3.set_build_consensus_matrix(sc.build_consensus_matrix)
+    s3.set_consensus_clustering(partial(sc.consensus_clustering, n_components=k))
+    s3.apply()
+    return s3
+
+
+def test_sc3_pipeline_labels_bit_exact_vs_reference(kernels, mixed, sc3g):
+    """cmd_target.py:220-242 wiring on the mixed default target data, same seed as the reference run."""
+    k, pc, seed = int(sc3g["k"]), [int(v) for v in sc3g["pc_range"]], int(sc3g["seed"])
+    s3 = _run_sc3(mixed, ["euclidean"], ["pca"], k, pc, seed)
+    np.testing.assert_array_equal(s3.cluster_labels, sc3g["labels_euclid_pca"])
+    np.testing.assert_array_equal(s3.dists, sc3g["cdists_euclid_pca"])
+    s3 = _run_sc3(mixed, ["euclidean", "pearson", "spearman"], ["pca", "spectral"], k, pc, seed)
+    np.testing.assert_array_equal(s3.cluster_labels, sc3g["labels_all"])
+    np.testing.assert_array_equal(s3.dists, sc3g["cdists_all"])
+
+
+def test_sc3_consensus_mode1_and_plain_callables(kernels, mixed, sc3g):
+    """The plug-in API accepts arbitrary callables (here the oracle's) and consensus_mode=1."""
+    from scrna_b200 import SC3Clustering
+    from scrna_b200 import sc3_clustering_impl as sc
+    k, pc = int(sc3g["k"]), [int(v) for v in sc3g["pc_range"]]
+    np.random.seed(5)
+    s3 = SC3Clustering(mixed, None, pc_range=pc, sub_sample=True, consensus_mode=1)
+    s3.add_distance_calculation(lambda X, ids: so.distances(X, "euclidean"))
+    s3.add_dimred_calculation(partial(sc.transformations, components=pc[1], method="pca"))
+    s3.add_intermediate_clustering(partial(sc.intermediate_kmeans_clustering, k=k))
+    s3.set_build_consensus_matrix(sc.build_consensus_matrix)
+    s3.set_consensus_clustering(partial(sc.consensus_clustering, n_components=k))
+    s3.apply()
+    assert s3.cluster_labels.shape == (100,) and len(np.unique(s3.cluster_labels)) == k
