@@ -1,0 +1,42 @@
+"""BASELINE.json configs[0]/[1] end to end on the GPU: source dictionary (NmfClustering_initW) -> target
+transfer + mixed data (DaNmfClustering) -> SC3 consensus clustering, all through the reference's class API,
+compared with the reference's own outputs (tests/golden)."""
+from functools import partial
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_source_to_target_to_sc3_labels_match_reference(kernels, default_sim, golden):
+    from scrna_b200 import NmfClustering_initW, DaNmfClustering, SC3Clustering
+    from scrna_b200 import sc3_clustering_impl as sc
+    g_t, g_s = golden("transfer"), golden("sc3")
+    gene_ids = default_sim["gene_ids"]
+    src = NmfClustering_initW(default_sim["src"], gene_ids, 7, default_sim["src_labels"])
+    src.apply(k=7, alpha=10., l1=0.75, max_iter=4000, rel_err=1e-3)
+    # cmd_source.py:208-212 pickles the model, cmd_target.py:188-196 reloads it: must survive pickling
+    import pickle
+    src = pickle.loads(pickle.dumps(src))
+
+    da = DaNmfClustering(src, default_sim["trg"].copy(), gene_ids, 7)
+    np.random.seed(1)
+    mixed, new_trg, trg = da.get_mixed_data(mix=0.5)
+    np.testing.assert_array_equal(da.cluster_labels, g_t["labels"])
+    assert np.linalg.norm(mixed - g_t["mixed"]) / np.linalg.norm(g_t["mixed"]) < 1e-4
+
+    k, pc, seed = int(g_s["k"]), [int(v) for v in g_s["pc_range"]], int(g_s["seed"])
+    for dists, transfs, key in ((["euclidean"], ["pca"], "labels_euclid_pca"),
+                                (["euclidean", "pearson", "spearman"], ["pca", "spectral"], "labels_all")):
+        np.random.seed(seed)
+        s3 = SC3Clustering(mixed, gene_ids, pc_range=pc, sub_sample=True, consensus_mode=0)
+        for d in dists:
+            s3.add_distance_calculation(partial(sc.distances, metric=d))
+        for t in transfs:
+            s3.add_dimred_calculation(partial(sc.transformations, components=pc[1], method=t))
+        s3.add_intermediate_clustering(partial(sc.intermediate_kmeans_clustering, k=k))
+        s3.set_build_consensus_matrix(sc.build_consensus_matrix)
+        s3.set_consensus_clustering(partial(sc.consensus_clustering, n_components=k))
+        s3.apply()
+        np.testing.assert_array_equal(s3.cluster_labels, g_s[key])

@@ -67,7 +67,8 @@ def test_transformations_vs_reference(ops, sc3g, metric, method):
     sgn = np.sign((V * ref).sum(axis=0))
     np.testing.assert_allclose(V * sgn, ref, rtol=0, atol=1e-8)
     assert rebuilt.shape == D.shape
-    assert ops.jacobi_sweeps < 30
+    from scrna_b200.sc3_device import default_ops
+    assert default_ops().jacobi_sweeps < 30
 
 
 def test_jacobi_on_random_matrices(ops):
