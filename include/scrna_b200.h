@@ -85,7 +85,8 @@ int scrna_nmf_xht_partial(const float* X, int64_t ldx, int g, int64_t ncols, con
  * _multiplicative_update_h (_nmf.py:644) / W.T.dot(trg_data) (utils.py:201).
  * part: nsplit x kp x ldc fp32.  The kernel is orientation-agnostic: called on the resident
  * transposed copy X^T (cells x genes) with the cell factor's row-major shadow it yields (X.C^T)^T,
- * i.e. K1 without a cross-lane reduction -- this is the default K1 path. */
+ * i.e. K1 without a cross-lane reduction -- this is the default K1 path.
+ * variant 0: scalar FFMA inner loop; variant >= 1: packed fma.rn.f32x2 (FFMA2, sm_100), bit-identical. */
 int scrna_nmf_wtx_partial(const float* X, int64_t ldx, int g, int64_t ncols, const float* G32, int kp,
                           float* part, int64_t ldc, int nsplit, int variant,
                           const scrna_nmf_ctrl_t* ctrl, void* stream);
@@ -117,9 +118,15 @@ int scrna_nmf_gram(const double* F, int64_t rs, int64_t cs, int64_t rows, int k,
  *   viol_part: scrna_nmf_update_blocks(rows) doubles, per-block sums of |projected gradient|.
  */
 int scrna_nmf_update_blocks(int64_t rows);
+/* num_parts != NULL: the numerator is the fixed-order fp64 sum of `nsplit` fp32 sweep partials (each
+ * kp x ld) -- the reduce step fused into the epilogue (single-GPU path; with cell shards the reduced
+ * products must exist in the all-reduce buffer first, so `num` is used).
+ * gram_out != NULL: additionally out = F_new^T F_new (kp x kp), the Gram the NEXT half step needs (K4
+ * fused); gram_partials is scratch of scrna_nmf_update_blocks(rows) * kp*kp doubles. */
 int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t rows, int k, int kp, const double* num,
-                     const double* gram, double l1, double l2, const int32_t* perms, int perm_stride,
-                     int perm_offset, float* S32, float* T32, double* viol_part, scrna_nmf_ctrl_t* ctrl,
+                     const float* num_parts, int nsplit, const double* gram, double l1, double l2,
+                     const int32_t* perms, int perm_stride, int perm_offset, float* S32, float* T32,
+                     double* viol_part, double* gram_partials, double* gram_out, scrna_nmf_ctrl_t* ctrl,
                      void* stream);
 /* Build the fp32 shadows of a component-major fp64 master (initial factors). */
 int scrna_nmf_shadows(const double* F64, int64_t ld, int64_t rows, int k, int kp, float* S32, float* T32,

@@ -36,8 +36,8 @@ _SIGNATURES = {
     "scrna_nmf_gram_blocks": [],
     "scrna_nmf_gram": [c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_nmf_update_blocks": [c_i64],
-    "scrna_nmf_update": [c_int, c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_dbl, c_dbl,
-                         c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "scrna_nmf_update": [c_int, c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_dbl, c_dbl,
+                         c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_nmf_shadows": [c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr],
     "scrna_transpose_f32": [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr],
     "scrna_nmf_iter_end": [c_ptr, c_ptr, c_int, c_ptr, c_int, c_dbl, c_int, c_ptr],

@@ -109,7 +109,7 @@ xht_partial_kernel(const float* __restrict__ X, int64_t ldx, int g, int64_t ncol
 // K3: each lane owns C cells and KP x C accumulators; the gene-factor rows of the CTA's gene span
 // are staged in shared memory and broadcast to all lanes.
 // -------------------------------------------------------------------------------------------
-template <int KP, int C, int U>
+template <int KP, int C, int U, bool F2>
 __global__ void __launch_bounds__(256, 2)
 wtx_partial_kernel(const float* __restrict__ X, int64_t ldx, int g, int64_t ncols,
                    const float* __restrict__ G32, float* __restrict__ part, int64_t ldc,
@@ -124,11 +124,12 @@ wtx_partial_kernel(const float* __restrict__ X, int64_t ldx, int g, int64_t ncol
   int r_end = r_begin + rows_per_split;
   if (r_end > g) r_end = g;
 
-  float acc[KP][C];
+  // accumulators as component pairs (t, t+1): with F2 one packed fma.rn.f32x2 updates both
+  float2 acc[KP / 2][C];
 #pragma unroll
-  for (int t = 0; t < KP; ++t)
+  for (int t = 0; t < KP / 2; ++t)
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[t][c] = 0.f;
+    for (int c = 0; c < C; ++c) acc[t][c] = make_float2(0.f, 0.f);
 
   for (int t0 = r_begin; t0 < r_end; t0 += tile_rows) {
     const int nr = min(tile_rows, r_end - t0);
@@ -170,10 +171,17 @@ wtx_partial_kernel(const float* __restrict__ X, int64_t ldx, int g, int64_t ncol
           const float4 w = w4[t / 4];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            acc[t + 0][c] = fmaf(w.x, xa[u].v[c], acc[t + 0][c]);
-            acc[t + 1][c] = fmaf(w.y, xa[u].v[c], acc[t + 1][c]);
-            acc[t + 2][c] = fmaf(w.z, xa[u].v[c], acc[t + 2][c]);
-            acc[t + 3][c] = fmaf(w.w, xa[u].v[c], acc[t + 3][c]);
+            const float x = xa[u].v[c];
+            if constexpr (F2) {
+              const float2 xx = make_float2(x, x);
+              acc[t / 2][c] = __ffma2_rn(make_float2(w.x, w.y), xx, acc[t / 2][c]);
+              acc[t / 2 + 1][c] = __ffma2_rn(make_float2(w.z, w.w), xx, acc[t / 2 + 1][c]);
+            } else {
+              acc[t / 2][c].x = fmaf(w.x, x, acc[t / 2][c].x);
+              acc[t / 2][c].y = fmaf(w.y, x, acc[t / 2][c].y);
+              acc[t / 2 + 1][c].x = fmaf(w.z, x, acc[t / 2 + 1][c].x);
+              acc[t / 2 + 1][c].y = fmaf(w.w, x, acc[t / 2 + 1][c].y);
+            }
           }
         }
       }
@@ -188,7 +196,7 @@ wtx_partial_kernel(const float* __restrict__ X, int64_t ldx, int g, int64_t ncol
     for (int t = 0; t < KP; ++t) {
       Vec<C> o;
 #pragma unroll
-      for (int c = 0; c < C; ++c) o.v[c] = acc[t][c];
+      for (int c = 0; c < C; ++c) o.v[c] = (t & 1) ? acc[t / 2][c].y : acc[t / 2][c].x;
       o.store(out + (int64_t)t * ldc);
     }
   }
@@ -202,8 +210,8 @@ struct SweepCfg {
   // cells per lane so that KP * C <= 64 accumulators (K3) and the K1 register tile stays <= 64
   static constexpr int C = KP <= 16 ? 4 : (KP <= 32 ? 2 : 1);
   static constexpr int R = KP <= 8 ? 8 : (KP <= 16 ? 4 : (KP <= 32 ? 2 : 1));  // R*KP <= 64
-  static constexpr int CB = KP <= 8 ? 4 : (KP <= 16 ? 2 : 1);                  // K3: KP*CB <= 32..64
-  static constexpr int U = 8;
+  static constexpr int CB = KP <= 16 ? 4 : (KP <= 32 ? 2 : 1);                 // K3: KP*CB <= 64
+  static constexpr int U = KP <= 8 ? 8 : 4;                                    // rows in flight per lane
 };
 
 static int pick_splits(int64_t tiles, int64_t slots, int max_split) {
@@ -248,14 +256,19 @@ static int wtx_tile_rows(int rows_per_split) {
 
 template <int KP>
 static int wtx_launch(const float* X, int64_t ldx, int g, int64_t ncols, const float* G32, float* part,
-                      int64_t ldc, int nsplit, const NmfCtrl* ctrl, cudaStream_t st) {
+                      int64_t ldc, int nsplit, int variant, const NmfCtrl* ctrl, cudaStream_t st) {
   using Cfg = SweepCfg<KP>;
   const int rps = (int)ceil_div(g, nsplit);
   const int tr = wtx_tile_rows<KP>(rps);
   dim3 grid((unsigned)ceil_div(ncols, 8 * 32 * Cfg::CB), (unsigned)nsplit);
   const size_t smem = (size_t)tr * KP * sizeof(float);
-  wtx_partial_kernel<KP, Cfg::CB, Cfg::U><<<grid, 256, smem, st>>>(X, ldx, g, ncols, G32, part, ldc, rps,
-                                                                  tr, ctrl);
+  // variant 0: scalar FFMA; variant >= 1 (default): packed fma.rn.f32x2 (FFMA2), bit-identical results
+  if (variant >= 1)
+    wtx_partial_kernel<KP, Cfg::CB, Cfg::U, true><<<grid, 256, smem, st>>>(X, ldx, g, ncols, G32, part, ldc, rps,
+                                                                          tr, ctrl);
+  else
+    wtx_partial_kernel<KP, Cfg::CB, Cfg::U, false><<<grid, 256, smem, st>>>(X, ldx, g, ncols, G32, part, ldc, rps,
+                                                                           tr, ctrl);
   return last_launch_status();
 }
 
@@ -328,9 +341,8 @@ extern "C" int scrna_nmf_wtx_partial(const float* X, int64_t ldx, int g, int64_t
   if (!X || !G32 || !part || g <= 0 || ncols <= 0 || nsplit <= 0 || (ldx & 3) || (ldc & 3) ||
       (ncols & 3) || ncols > ldx || ncols > ldc)
     return SCRNA_ERR_BADARG;
-  (void)variant;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const NmfCtrl* c = reinterpret_cast<const NmfCtrl*>(ctrl);
-  SCRNA_DISPATCH_KP(kp, return wtx_launch<KP>(X, ldx, g, ncols, G32, part, ldc, nsplit, c, st));
+  SCRNA_DISPATCH_KP(kp, return wtx_launch<KP>(X, ldx, g, ncols, G32, part, ldc, nsplit, variant, c, st));
   return SCRNA_ERR_UNSUPPORTED;
 }

@@ -92,16 +92,20 @@ gram_partial_kernel(const double* __restrict__ F, int64_t rs, int64_t cs, int64_
   }
 }
 
-__global__ void gram_final_kernel(const double* __restrict__ partials, int nblk, int k, int kp,
-                                  double* __restrict__ out, const NmfCtrl* __restrict__ ctrl) {
+// one warp per output element: lanes stride over the block partials (fixed order), butterfly sum
+__global__ void __launch_bounds__(256)
+gram_final_kernel(const double* __restrict__ partials, int nblk, int k, int kp, double* __restrict__ out,
+                  const NmfCtrl* __restrict__ ctrl) {
   if (ctrl_done(ctrl)) return;
-  for (int o = threadIdx.x; o < kp * kp; o += blockDim.x) {
-    const int a = o / kp, b = o - a * kp;
-    double s = 0.0;
-    if (a < k && b < k)
-      for (int p = 0; p < nblk; ++p) s += partials[(int64_t)p * kp * kp + o];
-    out[o] = s;
-  }
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= kp * kp) return;
+  const int a = o / kp, b = o - a * kp;
+  double s = 0.0;
+  if (a < k && b < k)
+    for (int p = lane; p < nblk; p += 32) s += partials[(int64_t)p * kp * kp + o];
+  s = warp_sum(s);
+  if (lane == 0) out[o] = s;
 }
 
 // ---- factor update ---------------------------------------------------------------------------
@@ -114,10 +118,11 @@ __global__ void gram_final_kernel(const double* __restrict__ partials, int nblk,
 template <int SOLVER>
 __global__ void __launch_bounds__(UPD_THREADS)
 update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
-              const double* __restrict__ num, const double* __restrict__ gram, double l1, double l2,
+              const double* __restrict__ num, const float* __restrict__ num_parts, int nsplit,
+              const double* __restrict__ gram, double l1, double l2,
               const int32_t* __restrict__ perms, int perm_stride, int perm_offset,
               float* __restrict__ S32, float* __restrict__ T32, double* __restrict__ viol_part,
-              NmfCtrl* __restrict__ ctrl) {
+              double* __restrict__ gram_part_out, NmfCtrl* __restrict__ ctrl) {
   if (ctrl_done(ctrl)) return;
   extern __shared__ double smem[];
   double* sg = smem;                         // kp*kp Gram
@@ -144,7 +149,15 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
     for (int t = 0; t < k; ++t) {
       const int64_t e = (int64_t)t * ld + r;
       sw[t * UPD_THREADS + tid] = F64[e];
-      sn[t * UPD_THREADS + tid] = num[e];
+      double nv;
+      if (num_parts) {  // fixed-order fp64 sum of the sweep's split partials (kp x ld fp32 each)
+        nv = 0.0;
+        const int64_t stride = (int64_t)kp * ld;
+        for (int p = 0; p < nsplit; ++p) nv += (double)num_parts[(int64_t)p * stride + e];
+      } else {
+        nv = num[e];
+      }
+      sn[t * UPD_THREADS + tid] = nv;
     }
     if (SOLVER == SCRNA_SOLVER_MU) {
       // W *= XHt / (W.HHt + l1 + l2*W); the denominator uses the OLD row throughout
@@ -195,10 +208,26 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
     }
   }
   if (nan_seen) snan = 1;
+  if (gram_part_out && !live)
+    for (int t = 0; t < k; ++t) sw[t * UPD_THREADS + tid] = 0.0;
   const double bsum = block_sum(viol, scratch);  // contains __syncthreads
   if (tid == 0) {
     if (viol_part) viol_part[blockIdx.x] = bsum;
     if (snan && ctrl) atomicOr(&ctrl->flags, SCRNA_FLAG_NAN);
+  }
+  if (gram_part_out) {
+    // Gram of this block's NEW rows: the next half step needs F^T F (K4 fused into the epilogue)
+    double* gp = gram_part_out + (int64_t)blockIdx.x * kp * kp;
+    for (int o = tid; o < kp * kp; o += UPD_THREADS) {
+      const int a = o / kp, b = o - a * kp;
+      double acc = 0.0;
+      if (a < k && b < k) {
+        const double* ra = sw + a * UPD_THREADS;
+        const double* rb = sw + b * UPD_THREADS;
+        for (int q = 0; q < UPD_THREADS; ++q) acc = fma(ra[q], rb[q], acc);
+      }
+      gp[o] = acc;
+    }
   }
 }
 
@@ -341,17 +370,19 @@ extern "C" int scrna_nmf_gram(const double* F, int64_t rs, int64_t cs, int64_t r
   const size_t smem = (size_t)GRAM_TILE * (k + 1) * sizeof(double);
   cudaStream_t st = (cudaStream_t)stream;
   gram_partial_kernel<<<nblk, GRAM_THREADS, smem, st>>>(F, rs, cs, rows, k, kp, partials, (const NmfCtrl*)ctrl);
-  gram_final_kernel<<<1, 256, 0, st>>>(partials, nblk, k, kp, out, (const NmfCtrl*)ctrl);
+  gram_final_kernel<<<(unsigned)ceil_div(kp * kp, 8), 256, 0, st>>>(partials, nblk, k, kp, out, (const NmfCtrl*)ctrl);
   return last_launch_status();
 }
 
 extern "C" int scrna_nmf_update_blocks(int64_t rows) { return (int)ceil_div(rows, UPD_THREADS); }
 
 extern "C" int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t rows, int k, int kp,
-                                const double* num, const double* gram, double l1, double l2,
-                                const int32_t* perms, int perm_stride, int perm_offset, float* S32, float* T32,
-                                double* viol_part, scrna_nmf_ctrl_t* ctrl, void* stream) {
-  if (!F64 || !num || !gram || rows <= 0 || ld < rows || k <= 0 || k > kp || kp > SCRNA_MAX_K || (kp & 3))
+                                const double* num, const float* num_parts, int nsplit, const double* gram,
+                                double l1, double l2, const int32_t* perms, int perm_stride, int perm_offset,
+                                float* S32, float* T32, double* viol_part, double* gram_partials, double* gram_out,
+                                scrna_nmf_ctrl_t* ctrl, void* stream) {
+  if (!F64 || (!num && !num_parts) || (num_parts && nsplit <= 0) || !gram || rows <= 0 || ld < rows || k <= 0 ||
+      k > kp || kp > SCRNA_MAX_K || (kp & 3) || (gram_out && !gram_partials))
     return SCRNA_ERR_BADARG;
   const size_t smem = ((size_t)kp * kp + 2 * (size_t)k * UPD_THREADS) * sizeof(double);
   const int nblk = (int)ceil_div(rows, UPD_THREADS);
@@ -363,15 +394,20 @@ extern "C" int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t row
     attr_set = true;
   }
   if (solver == SCRNA_SOLVER_MU)
-    update_kernel<SCRNA_SOLVER_MU><<<nblk, UPD_THREADS, smem, st>>>(F64, ld, rows, k, kp, num, gram, l1, l2, perms,
-                                                                  perm_stride, perm_offset, S32, T32, viol_part,
-                                                                  (NmfCtrl*)ctrl);
+    update_kernel<SCRNA_SOLVER_MU><<<nblk, UPD_THREADS, smem, st>>>(F64, ld, rows, k, kp, num, num_parts, nsplit, gram,
+                                                                  l1, l2, perms, perm_stride, perm_offset, S32, T32,
+                                                                  viol_part, gram_partials, (NmfCtrl*)ctrl);
   else if (solver == SCRNA_SOLVER_CD)
-    update_kernel<SCRNA_SOLVER_CD><<<nblk, UPD_THREADS, smem, st>>>(F64, ld, rows, k, kp, num, gram, l1, l2, perms,
-                                                                  perm_stride, perm_offset, S32, T32, viol_part,
-                                                                  (NmfCtrl*)ctrl);
+    update_kernel<SCRNA_SOLVER_CD><<<nblk, UPD_THREADS, smem, st>>>(F64, ld, rows, k, kp, num, num_parts, nsplit, gram,
+                                                                  l1, l2, perms, perm_stride, perm_offset, S32, T32,
+                                                                  viol_part, gram_partials, (NmfCtrl*)ctrl);
   else
     return SCRNA_ERR_BADARG;
+  if (gram_out) {
+    const int warps = kp * kp;
+    gram_final_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(gram_partials, nblk, k, kp, gram_out,
+                                                                   (const NmfCtrl*)ctrl);
+  }
   return last_launch_status();
 }
 

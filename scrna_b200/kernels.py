@@ -43,7 +43,7 @@ class CudaKernels:
     def xht_partial(self, X, ldx, g, ncols, C32, ldc, kp, part, nsplit, ctrl, variant=0):
         self._call("scrna_nmf_xht_partial", X, ldx, g, ncols, C32, ldc, kp, part, nsplit, variant, ctrl, self._s())
 
-    def wtx_partial(self, X, ldx, g, ncols, G32, kp, part, ldc, nsplit, ctrl, variant=0):
+    def wtx_partial(self, X, ldx, g, ncols, G32, kp, part, ldc, nsplit, ctrl, variant=2):
         ev = self.sweep_events
         if ev is not None:
             a = self.torch.cuda.Event(enable_timing=True)
@@ -65,9 +65,12 @@ class CudaKernels:
         self._call("scrna_nmf_gram", F64, rs, cs, rows, k, kp, partials, out, ctrl, self._s())
 
     def update(self, solver, F64, ld, rows, k, kp, num, gram, l1, l2, perms, perm_stride, perm_offset, S32, T32,
-               viol_part, ctrl):
-        self._call("scrna_nmf_update", solver, F64, ld, rows, k, kp, num, gram, float(l1), float(l2),
-                   perms, perm_stride, perm_offset, S32, T32, viol_part, ctrl, self._s())
+               viol_part, ctrl, num_parts=None, nsplit=0, gram_partials=None, gram_out=None):
+        if gram_out is not None:
+            self.launches += 1
+        self._call("scrna_nmf_update", solver, F64, ld, rows, k, kp, num, num_parts, nsplit, gram, float(l1),
+                   float(l2), perms, perm_stride, perm_offset, S32, T32, viol_part, gram_partials, gram_out, ctrl,
+                   self._s())
 
     def shadows(self, F64, ld, rows, k, kp, S32, T32):
         self._call("scrna_nmf_shadows", F64, ld, rows, k, kp, S32, T32, self._s())

@@ -175,6 +175,10 @@ class NmfSolver:
         self.ctrl = t.zeros(16, dtype=t.int32, device=dev)
         self.res_part = t.zeros(max(1, kernels.residual_blocks(X.ncols, kp)), dtype=f64, device=dev)
         self.res_out = t.zeros(1, dtype=f64, device=dev)
+        self.gpartG = t.zeros(self.nblkG * kp * kp, dtype=f64, device=dev)
+        self.gpartC = t.zeros(self.nblkC * kp * kp, dtype=f64, device=dev)
+        self.fuse_reduce = True   # partial reduction + Gram fused into the update epilogues
+        self._g_num_from_R = True
         self.perms = None
 
     # ---- helpers ------------------------------------------------------------------------------
@@ -207,33 +211,52 @@ class NmfSolver:
         return G, C
 
     # ---- the two half steps -------------------------------------------------------------------
-    def _products_for_G(self, ctrl):
-        """R.xht = (X.C^T)^T (this shard), R.cct = C.C^T (this shard); the all-reduce follows."""
+    def _gram_C(self, ctrl):
+        self.kn.gram(self.C64, 1, self.ldn, max(self.X.n, 1), self.k, self.kp, self.gram_part, self.R_cct, ctrl)
+
+    def _gram_G(self, ctrl):
+        self.kn.gram(self.G64, 1, self.ldg, self.X.g, self.k, self.kp, self.gram_part, self.gtg, ctrl)
+
+    def _products_for_G(self, ctrl, with_gram=False):
+        """K1: this shard's (X.C^T)^T as split partials PA (and, when they must travel through the
+        all-reduce buffer, their fixed-order sum R.xht).  R.cct = C.C^T is produced by the previous
+        cell-factor epilogue (or by _gram_C for the initial / a fixed C)."""
         kn, X, kp = self.kn, self.X, self.kp
         if self.XT is not None:
             XT = self.XT
             kn.wtx_partial(XT.data, XT.ldx, XT.g, self.gcols, self.Cs32, kp, self.PA, self.ldg, self.SA, ctrl)
-            kn.reduce_cols(self.PA, self.SA, kp, self.ldg, self.gcols, self.R_xht, ctrl)
+            if self._g_num_from_R:
+                kn.reduce_cols(self.PA, self.SA, kp, self.ldg, self.gcols, self.R_xht, ctrl)
         else:
             kn.xht_partial(X.data, X.ldx, X.g, X.ncols, self.Ct32, self.ldn, kp, self.PA, self.SA, ctrl)
             kn.reduce_rows(self.PA, self.SA, X.g, kp, self.R_xht, self.ldg, ctrl)
-        kn.gram(self.C64, 1, self.ldn, max(X.n, 1), self.k, kp, self.gram_part, self.R_cct, ctrl)
+        if with_gram:
+            self._gram_C(ctrl)
 
     def _allreduce_R(self):
         if self.comm is not None:
             self.comm.all_reduce(self.R)
 
     def _update_G(self, solver, l1, l2, stride, offset, ctrl):
-        self.kn.update(solver, self.G64, self.ldg, self.X.g, self.k, self.kp, self.R_xht, self.R_cct, l1, l2,
-                       self.perms, stride, offset, self.Gs32, None, self.violG, ctrl)
+        fused = not self._g_num_from_R
+        self.kn.update(solver, self.G64, self.ldg, self.X.g, self.k, self.kp,
+                       None if fused else self.R_xht, self.R_cct, l1, l2, self.perms, stride, offset,
+                       self.Gs32, None, self.violG, ctrl,
+                       num_parts=self.PA if fused else None, nsplit=self.SA if fused else 0,
+                       gram_partials=self.gpartG, gram_out=self.gtg)
 
     def _half_C(self, solver, l1, l2, stride, offset, ctrl):
         kn, X, kp = self.kn, self.X, self.kp
-        kn.gram(self.G64, 1, self.ldg, X.g, self.k, kp, self.gram_part, self.gtg, ctrl)
         kn.wtx_partial(X.data, X.ldx, X.g, X.ncols, self.Gs32, kp, self.PB, self.ldn, self.SB, ctrl)
-        kn.reduce_cols(self.PB, self.SB, kp, self.ldn, X.ncols, self.NB, ctrl)
-        kn.update(solver, self.C64, self.ldn, max(X.n, 1), self.k, kp, self.NB, self.gtg, l1, l2,
-                  self.perms, stride, offset, self.Cs32, self.Ct32, self.violC, ctrl)
+        if self.fuse_reduce:
+            kn.update(solver, self.C64, self.ldn, max(X.n, 1), self.k, kp, None, self.gtg, l1, l2,
+                      self.perms, stride, offset, self.Cs32, self.Ct32, self.violC, ctrl,
+                      num_parts=self.PB, nsplit=self.SB, gram_partials=self.gpartC, gram_out=self.R_cct)
+        else:
+            kn.reduce_cols(self.PB, self.SB, kp, self.ldn, X.ncols, self.NB, ctrl)
+            kn.update(solver, self.C64, self.ldn, max(X.n, 1), self.k, kp, self.NB, self.gtg, l1, l2,
+                      self.perms, stride, offset, self.Cs32, self.Ct32, self.violC, ctrl,
+                      gram_partials=self.gpartC, gram_out=self.R_cct)
 
     def frobenius_error(self):
         """||X - G.C||_F over all shards (sklearn _beta_divergence(..., square_root=True))."""
@@ -282,12 +305,18 @@ class NmfSolver:
         offC = 0 if (first == "C" or not update_G) else 1
         cd_tol = float(tol) if solver == "cd" else -1.0
 
+        # Grams of the initial factors (afterwards every epilogue emits the Gram of what it just wrote)
+        self._gram_C(None)
+        self._gram_G(None)
         # a fixed factor makes its products constant: compute them once
+        # R.xht must be materialised when it travels through the all-reduce, when the low-memory K1
+        # produced row-major partials, or when C is fixed (then it is computed once and reused)
+        self._g_num_from_R = (self.comm is not None) or (self.XT is None) or (not update_C) or (not self.fuse_reduce)
         if not update_C:
             self._products_for_G(None)
             self._allreduce_R()
-        if not update_G:
-            kn.gram(self.G64, 1, self.ldg, self.X.g, self.k, self.kp, self.gram_part, self.gtg, None)
+
+        use_iter_end = solver == "cd"
 
         def one_iteration():
             if first == "G":
@@ -316,7 +345,8 @@ class NmfSolver:
                 vb, nb = (self.R_scal, 1) if self.comm is not None else (self.violC, self.nblkC)
             else:
                 vb, nb = None, 0
-            kn.iter_end(ctrl, va, na, vb, nb, cd_tol, max_iter)
+            if use_iter_end:
+                kn.iter_end(ctrl, va, na, vb, nb, cd_tol, max_iter)
 
         self.step = one_iteration
         self._plan = dict(solver=solver, tol=float(tol), max_iter=max_iter)

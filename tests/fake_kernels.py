@@ -71,11 +71,14 @@ class FakeKernels:
         o[:k, :k] = F @ F.T
 
     def update(self, solver, F64, ld, rows, k, kp, num, gram, l1, l2, perms, perm_stride, perm_offset, S32, T32,
-               viol_part, ctrl):
+               viol_part, ctrl, num_parts=None, nsplit=0, gram_partials=None, gram_out=None):
         if self._done(ctrl): return
         F = _np(F64)
         W = np.ascontiguousarray(F[:k, :rows].T)
-        N = _np(num).reshape(kp, ld)[:k, :rows].T.copy()
+        if num_parts is not None:
+            N = _np(num_parts).astype(np.float64).sum(axis=0).reshape(kp, ld)[:k, :rows].T.copy()
+        else:
+            N = _np(num).reshape(kp, ld)[:k, :rows].T.copy()
         G = _np(gram).reshape(kp, kp)[:k, :k].copy()
         if solver == 1:
             it = int(ctrl[0]) if ctrl is not None else 0
@@ -92,6 +95,9 @@ class FakeKernels:
             if viol_part is not None: _np(viol_part)[:] = 0
         F[:k, :rows] = W.T
         self.shadows(F64, ld, rows, k, kp, S32, T32)
+        if gram_out is not None:
+            o = _np(gram_out).reshape(kp, kp); o[:] = 0
+            o[:k, :k] = W.T @ W
 
     def iter_end(self, ctrl, viol_a, na, viol_b, nb, tol, max_iter):
         c = _np(ctrl)

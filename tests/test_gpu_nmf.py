@@ -40,7 +40,8 @@ def test_sweeps_match_fp64_products(kernels, g, n, k, transpose_copy):
     if transpose_copy:
         np.testing.assert_array_equal(slv.XT.data[:n, :g].cpu().numpy(), X.T.astype(np.float32))
         assert float(slv.XT.data[:, g:].abs().sum().cpu()) == 0.0
-    slv._products_for_G(None)
+    slv._g_num_from_R = True
+    slv._products_for_G(None, with_gram=True)
     torch.cuda.synchronize()
     xht = slv.R_xht.view(slv.kp, slv.ldg)[:k, :g].cpu().numpy().T
     cct = slv.R_cct.view(slv.kp, slv.kp)[:k, :k].cpu().numpy()
@@ -63,8 +64,9 @@ def test_sweeps_match_fp64_products(kernels, g, n, k, transpose_copy):
     assert abs(slv.frobenius_error() - np.linalg.norm(X - G @ C)) / np.linalg.norm(X - G @ C) < 2e-5
 
 
+@pytest.mark.parametrize("fused_parts", [False, True])
 @pytest.mark.parametrize("solver", ["cd", "mu"])
-def test_single_update_matches_oracle(kernels, solver):
+def test_single_update_matches_oracle(kernels, solver, fused_parts):
     """One half step with exact fp64 inputs: the epilogue alone, compared at fp64 rounding level."""
     import scrna_b200._lib as L
     torch = kernels.torch
@@ -91,9 +93,22 @@ def test_single_update_matches_oracle(kernels, solver):
     viol = torch.zeros(kernels.update_blocks(rows), dtype=torch.float64, device=dev)
     ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
     code = L.SOLVER_CD if solver == "cd" else L.SOLVER_MU
-    kernels.update(code, F64, ld, rows, k, kp, num, gram, l1, l2, perms, 1, 0, S32, T32, viol, ctrl)
+    gpart = torch.zeros(kernels.update_blocks(rows) * kp * kp, dtype=torch.float64, device=dev)
+    gout = torch.zeros(kp * kp, dtype=torch.float64, device=dev)
+    if fused_parts:
+        # the same numerator presented as 3 fp32 split partials (exactly representable pieces)
+        N32 = np.round(N * 0.25 * 64) / 64
+        parts = np.stack([N32, N32, N - 2 * N32]).astype(np.float32)
+        N = parts.astype(np.float64).sum(axis=0)
+        XHt = N[:k, :rows].T.copy()
+        kernels.update(code, F64, ld, rows, k, kp, None, gram, l1, l2, perms, 1, 0, S32, T32, viol, ctrl,
+                       num_parts=torch.from_numpy(parts).to(dev), nsplit=3, gram_partials=gpart, gram_out=gout)
+    else:
+        kernels.update(code, F64, ld, rows, k, kp, num, gram, l1, l2, perms, 1, 0, S32, T32, viol, ctrl,
+                       gram_partials=gpart, gram_out=gout)
     torch.cuda.synchronize()
     got = F64.cpu().numpy()[:k, :rows].T
+    np.testing.assert_allclose(gout.view(kp, kp)[:k, :k].cpu().numpy(), got.T @ got, rtol=1e-12)
     Wref = W.copy()
     if solver == "cd":
         H2 = HHt.copy(); H2.flat[:: k + 1] += l2

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--sa", type=int, nargs="*", default=[])
     ap.add_argument("--sb", type=int, nargs="*", default=[])
     ap.add_argument("--lowmem", action="store_true")
+    ap.add_argument("--variants", type=int, nargs="*", default=[0])
     args = ap.parse_args()
     kn = default_kernels()
     g, n = args.genes, args.cells
@@ -61,10 +62,15 @@ def main():
         sa_list = args.sa or [slv.SA]
         sb_list = args.sb or [slv.SB]
         for sb in sb_list:
+          for var in args.variants:
             PB = torch.zeros((sb, kp, slv.ldn), dtype=torch.float32, device=dev)
-            med, best = timeit(lambda: kn.wtx_partial(X, ldx, g, dm.ncols, slv.Gs32, kp, PB, slv.ldn, sb, None))
-            out.append(dict(kernel="sweep_X(K3)", k=k, nsplit=sb, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
+            med, best = timeit(lambda: kn.wtx_partial(X, ldx, g, dm.ncols, slv.Gs32, kp, PB, slv.ldn, sb, None, variant=var))
+            out.append(dict(kernel="sweep_X(K3)", k=k, variant=var, nsplit=sb, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
             print(out[-1], flush=True)
+            if var > 0:
+                ref = torch.zeros_like(PB)
+                kn.wtx_partial(X, ldx, g, dm.ncols, slv.Gs32, kp, ref, slv.ldn, sb, None, variant=0)
+                print("   variant", var, "max abs diff vs variant 0:", float((ref - PB).abs().max()), flush=True)
         XT = slv.XT
         for sa in sa_list:
             PA = torch.zeros((sa, kp, slv.ldg), dtype=torch.float32, device=dev)
@@ -86,6 +92,9 @@ def main():
             slv._load_factors(G0, C0)
             perms = np.zeros((64, kp), dtype=np.int32); perms[:, :k] = np.arange(k)
             slv.perms = torch.from_numpy(perms).to(dev)
+
+            slv._g_num_from_R = False
+            slv._gram_C(None); slv._gram_G(None)
 
             def it():
                 slv._products_for_G(None)
