@@ -146,18 +146,28 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
   double viol = 0.0;
   bool nan_seen = false;
   if (live) {
-    for (int t = 0; t < k; ++t) {
-      const int64_t e = (int64_t)t * ld + r;
-      sw[t * UPD_THREADS + tid] = F64[e];
-      double nv;
-      if (num_parts) {  // fixed-order fp64 sum of the sweep's split partials (kp x ld fp32 each)
-        nv = 0.0;
-        const int64_t stride = (int64_t)kp * ld;
-        for (int p = 0; p < nsplit; ++p) nv += (double)num_parts[(int64_t)p * stride + e];
-      } else {
-        nv = num[e];
+    for (int t = 0; t < k; ++t) sw[t * UPD_THREADS + tid] = F64[(int64_t)t * ld + r];
+    if (num_parts) {
+      // fixed-order fp64 sum of the sweep's split partials (kp x ld fp32 each); eight components at a
+      // time so that 8 x (unrolled splits) independent loads are in flight per thread
+      const int64_t stride = (int64_t)kp * ld;
+      for (int t0 = 0; t0 < k; t0 += 8) {
+        double a8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a8[u] = 0.0;
+        const float* base = num_parts + (int64_t)t0 * ld + r;
+#pragma unroll 4
+        for (int p = 0; p < nsplit; ++p) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (t0 + u < k) a8[u] += (double)base[(int64_t)p * stride + (int64_t)u * ld];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (t0 + u < k) sn[(t0 + u) * UPD_THREADS + tid] = a8[u];
       }
-      sn[t * UPD_THREADS + tid] = nv;
+    } else {
+      for (int t = 0; t < k; ++t) sn[t * UPD_THREADS + tid] = num[(int64_t)t * ld + r];
     }
     if (SOLVER == SCRNA_SOLVER_MU) {
       // W *= XHt / (W.HHt + l1 + l2*W); the denominator uses the OLD row throughout
