@@ -189,7 +189,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -283,9 +283,9 @@ def run_gpu(args):
     # ---- end to end through the public API, from pinned host buffers -----------------------------
     if args.no_e2e:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": ms / args.steps, "roofline": roofline, "gpu_launches": launches,
-                              "note": "profiling run (--no-e2e): not a bench line"}))
+            emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                  "ms_per_step": ms / args.steps, "roofline": roofline, "gpu_launches": launches,
+                  "note": "profiling run (--no-e2e): not a bench line"})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -350,12 +350,31 @@ def run_gpu(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner when
+    NCCL_DEBUG is set in the environment) are sent to stderr; the JSON line goes to the saved fd."""
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+_OUT = None
+
+
+def emit(line):
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

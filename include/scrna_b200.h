@@ -91,6 +91,29 @@ int scrna_nmf_wtx_partial(const float* X, int64_t ldx, int g, int64_t ncols, con
                           float* part, int64_t ldc, int nsplit, int variant,
                           const scrna_nmf_ctrl_t* ctrl, void* stream);
 
+/* K1/K3 on the tensor cores (tcgen05.mma kind::tf32, accumulators in tensor memory, X staged by bulk
+ * TMA): same contract and partial layout as scrna_nmf_wtx_partial for kp in {16, 32, 48, 64}, where the
+ * FP32 pipe can no longer keep up with HBM.  The factor is passed as its 3xTF32 operand shadow Fs
+ * ([hi | lo], scrna_nmf_tc_shadow_elems(g, kp) floats, K-major MMA operand layout
+ * [(r/4)][n < 2kp][r%4]) written by scrna_nmf_tc_shadow; products are Xh.[Fh|Fl] + Xl.Fh accumulated in
+ * fp32 and drained from tensor memory every 32 stages (512 rows) so that the accumulator's truncation
+ * bias stays at the fp32 rounding level.
+ * nsplit must come from scrna_nmf_wtx_tc_splits (every row span non-empty, spans multiples of 16 rows).
+ * flags: 32 = X is TF32-exact (scrna_tf32_inexact reported 0); bits 1-4: bring-up probes; bits 8-23: drain
+ * period override in stages. */
+int scrna_nmf_tc_supported(int kp);
+int64_t scrna_nmf_tc_shadow_elems(int64_t rows, int kp);
+int scrna_nmf_wtx_tc_splits(int g, int64_t ncols, int kp);
+int scrna_nmf_wtx_partial_tc(const float* X, int64_t ldx, int g, int64_t ncols, const float* Fs, int kp,
+                             float* part, int64_t ldc, int nsplit, int flags, const scrna_nmf_ctrl_t* ctrl,
+                             void* stream);
+/* inexact[0] = 1 if any of the `count` (multiple of 4) fp32 values at X carries mantissa bits below TF32's
+ * 10, else 0.  Raw counts < 2048 are exact: then Xl == 0 and the caller passes flag 32 to
+ * scrna_nmf_wtx_partial_tc, which skips the Xl product. */
+int scrna_tf32_inexact(const float* X, int64_t count, int32_t* inexact, void* stream);
+/* [hi | lo] TF32 operand shadow of a component-major fp64 master (kp x ld, element [t*ld + r]). */
+int scrna_nmf_tc_shadow(const double* F64, int64_t ld, int64_t rows, int k, int kp, float* Fs, void* stream);
+
 /* Sum the K1 partials over the splits in fixed order into fp64, component-major: out[t*ld + i]. */
 int scrna_nmf_reduce_rows(const float* part, int nsplit, int g, int kp, double* out, int64_t ld,
                           const scrna_nmf_ctrl_t* ctrl, void* stream);
@@ -115,6 +138,8 @@ int scrna_nmf_gram(const double* F, int64_t rs, int64_t cs, int64_t rows, int k,
  *              perm_offset) * kp .. +k) is the pre-drawn RandomState stream;
  *   S32  : fp32 row-major shadow (rows x kp, padding components zero) read by the next sweep;
  *   T32  : optional fp32 component-major shadow (kp x ld) read by scrna_residual / K1 variant 0;
+ *   TC32 : optional [hi | lo] TF32 operand shadow read by scrna_nmf_wtx_partial_tc (rows and components
+ *          beyond `rows` / `k` must have been zeroed once, e.g. by scrna_nmf_tc_shadow);
  *   viol_part: scrna_nmf_update_blocks(rows) doubles, per-block sums of |projected gradient|.
  */
 int scrna_nmf_update_blocks(int64_t rows);
@@ -125,7 +150,7 @@ int scrna_nmf_update_blocks(int64_t rows);
  * fused); gram_partials is scratch of scrna_nmf_update_blocks(rows) * kp*kp doubles. */
 int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t rows, int k, int kp, const double* num,
                      const float* num_parts, int nsplit, const double* gram, double l1, double l2,
-                     const int32_t* perms, int perm_stride, int perm_offset, float* S32, float* T32,
+                     const int32_t* perms, int perm_stride, int perm_offset, float* S32, float* T32, float* TC32,
                      double* viol_part, double* gram_partials, double* gram_out, scrna_nmf_ctrl_t* ctrl,
                      void* stream);
 /* Build the fp32 shadows of a component-major fp64 master (initial factors). */

@@ -31,13 +31,19 @@ _SIGNATURES = {
     "scrna_nmf_wtx_splits": [c_int, c_i64, c_int],
     "scrna_nmf_xht_partial": [c_ptr, c_i64, c_int, c_i64, c_ptr, c_i64, c_int, c_ptr, c_int, c_int, c_ptr, c_ptr],
     "scrna_nmf_wtx_partial": [c_ptr, c_i64, c_int, c_i64, c_ptr, c_int, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr],
+    "scrna_nmf_tc_supported": [c_int],
+    "scrna_nmf_wtx_tc_splits": [c_int, c_i64, c_int],
+    "scrna_nmf_wtx_partial_tc": [c_ptr, c_i64, c_int, c_i64, c_ptr, c_int, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr],
+    "scrna_nmf_tc_shadow": [c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr],
+    "scrna_nmf_tc_shadow_elems": [c_i64, c_int],
+    "scrna_tf32_inexact": [c_ptr, c_i64, c_ptr, c_ptr],
     "scrna_nmf_reduce_rows": [c_ptr, c_int, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr],
     "scrna_nmf_reduce_cols": [c_ptr, c_int, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "scrna_nmf_gram_blocks": [],
     "scrna_nmf_gram": [c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_nmf_update_blocks": [c_i64],
     "scrna_nmf_update": [c_int, c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_dbl, c_dbl,
-                         c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+                         c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_nmf_shadows": [c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr],
     "scrna_transpose_f32": [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr],
     "scrna_nmf_iter_end": [c_ptr, c_ptr, c_int, c_ptr, c_int, c_dbl, c_int, c_ptr],
@@ -81,7 +87,11 @@ _SIGNATURES = {
 
 # entry points that return a count / version instead of a status code
 _VALUE_RETURNING = {"scrna_abi_version", "scrna_nmf_xht_splits", "scrna_nmf_wtx_splits", "scrna_nmf_gram_blocks",
-                    "scrna_nmf_update_blocks", "scrna_residual_blocks"}
+                    "scrna_nmf_update_blocks", "scrna_residual_blocks", "scrna_nmf_tc_supported", "scrna_nmf_wtx_tc_splits",
+                    "scrna_nmf_tc_shadow_elems"}
+
+
+_RETURNS_I64 = {"scrna_nmf_tc_shadow_elems"}
 
 
 class ScrnaError(RuntimeError):
@@ -109,7 +119,7 @@ def load():
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.argtypes = argtypes
-        fn.restype = c_int
+        fn.restype = c_i64 if name in _RETURNS_I64 else c_int
     _lib = lib
     return lib
 

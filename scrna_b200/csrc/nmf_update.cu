@@ -121,8 +121,8 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
               const double* __restrict__ num, const float* __restrict__ num_parts, int nsplit,
               const double* __restrict__ gram, double l1, double l2,
               const int32_t* __restrict__ perms, int perm_stride, int perm_offset,
-              float* __restrict__ S32, float* __restrict__ T32, double* __restrict__ viol_part,
-              double* __restrict__ gram_part_out, NmfCtrl* __restrict__ ctrl) {
+              float* __restrict__ S32, float* __restrict__ T32, float* __restrict__ TC32,
+              double* __restrict__ viol_part, double* __restrict__ gram_part_out, NmfCtrl* __restrict__ ctrl) {
   if (ctrl_done(ctrl)) return;
   extern __shared__ double smem[];
   double* sg = smem;                         // kp*kp Gram
@@ -204,6 +204,16 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
       const int64_t e = (int64_t)t * ld + r;
       F64[e] = v;
       if (T32) T32[e] = (float)v;
+    }
+    if (TC32) {
+      // [hi | lo] TF32 operand shadow of the tensor-core sweep (nmf_sweep_tc.cu): [(r/4)][n < 2kp][r%4]
+      float* base = TC32 + ((r >> 2) * 2 * kp) * 4 + (r & 3);
+      for (int t = 0; t < k; ++t) {
+        const double v = sw[t * UPD_THREADS + tid];
+        const float h = __uint_as_float(__float_as_uint((float)v) & 0xffffe000u);
+        base[t * 4] = h;
+        base[(kp + t) * 4] = __uint_as_float(__float_as_uint((float)(v - (double)h)) & 0xffffe000u);
+      }
     }
     if (S32) {
       float* srow = S32 + r * kp;
@@ -389,8 +399,8 @@ extern "C" int scrna_nmf_update_blocks(int64_t rows) { return (int)ceil_div(rows
 extern "C" int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t rows, int k, int kp,
                                 const double* num, const float* num_parts, int nsplit, const double* gram,
                                 double l1, double l2, const int32_t* perms, int perm_stride, int perm_offset,
-                                float* S32, float* T32, double* viol_part, double* gram_partials, double* gram_out,
-                                scrna_nmf_ctrl_t* ctrl, void* stream) {
+                                float* S32, float* T32, float* TC32, double* viol_part, double* gram_partials,
+                                double* gram_out, scrna_nmf_ctrl_t* ctrl, void* stream) {
   if (!F64 || (!num && !num_parts) || (num_parts && nsplit <= 0) || !gram || rows <= 0 || ld < rows || k <= 0 ||
       k > kp || kp > SCRNA_MAX_K || (kp & 3) || (gram_out && !gram_partials))
     return SCRNA_ERR_BADARG;
@@ -406,11 +416,11 @@ extern "C" int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t row
   if (solver == SCRNA_SOLVER_MU)
     update_kernel<SCRNA_SOLVER_MU><<<nblk, UPD_THREADS, smem, st>>>(F64, ld, rows, k, kp, num, num_parts, nsplit, gram,
                                                                   l1, l2, perms, perm_stride, perm_offset, S32, T32,
-                                                                  viol_part, gram_partials, (NmfCtrl*)ctrl);
+                                                                  TC32, viol_part, gram_partials, (NmfCtrl*)ctrl);
   else if (solver == SCRNA_SOLVER_CD)
     update_kernel<SCRNA_SOLVER_CD><<<nblk, UPD_THREADS, smem, st>>>(F64, ld, rows, k, kp, num, num_parts, nsplit, gram,
                                                                   l1, l2, perms, perm_stride, perm_offset, S32, T32,
-                                                                  viol_part, gram_partials, (NmfCtrl*)ctrl);
+                                                                  TC32, viol_part, gram_partials, (NmfCtrl*)ctrl);
   else
     return SCRNA_ERR_BADARG;
   if (gram_out) {

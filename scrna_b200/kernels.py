@@ -54,6 +54,35 @@ class CudaKernels:
             b.record()
             ev.append((a, b, int(g) * int(ncols) * 4))
 
+    def tc_supported(self, kp):
+        return bool(_lib.call("scrna_nmf_tc_supported", kp))
+
+    def wtx_tc_splits(self, g, ncols, kp):
+        return _lib.call("scrna_nmf_wtx_tc_splits", g, ncols, kp)
+
+    def tc_shadow_elems(self, rows, kp):
+        return _lib.call("scrna_nmf_tc_shadow_elems", rows, kp)
+
+    def wtx_partial_tc(self, X, ldx, g, ncols, Fs, kp, part, ldc, nsplit, ctrl, flags=0):
+        ev = self.sweep_events
+        if ev is not None:
+            a = self.torch.cuda.Event(enable_timing=True)
+            b = self.torch.cuda.Event(enable_timing=True)
+            a.record()
+        self._call("scrna_nmf_wtx_partial_tc", X, ldx, g, ncols, Fs, kp, part, ldc, nsplit, flags, ctrl, self._s())
+        if ev is not None:
+            b.record()
+            ev.append((a, b, int(g) * int(ncols) * 4))
+
+    def tf32_exact(self, X):
+        """True if every element of the fp32 tensor is exactly representable in TF32."""
+        flag = self.torch.zeros(1, dtype=self.torch.int32, device=X.device)
+        self._call("scrna_tf32_inexact", X, X.numel(), flag, self._s())
+        return int(flag.item()) == 0
+
+    def tc_shadow(self, F64, ld, rows, k, kp, Fs):
+        self._call("scrna_nmf_tc_shadow", F64, ld, rows, k, kp, Fs, self._s())
+
     def reduce_rows(self, part, nsplit, g, kp, out, ld, ctrl):
         self._call("scrna_nmf_reduce_rows", part, nsplit, g, kp, out, ld, ctrl, self._s())
 
@@ -65,11 +94,11 @@ class CudaKernels:
         self._call("scrna_nmf_gram", F64, rs, cs, rows, k, kp, partials, out, ctrl, self._s())
 
     def update(self, solver, F64, ld, rows, k, kp, num, gram, l1, l2, perms, perm_stride, perm_offset, S32, T32,
-               viol_part, ctrl, num_parts=None, nsplit=0, gram_partials=None, gram_out=None):
+               viol_part, ctrl, num_parts=None, nsplit=0, gram_partials=None, gram_out=None, TC32=None):
         if gram_out is not None:
             self.launches += 1
         self._call("scrna_nmf_update", solver, F64, ld, rows, k, kp, num, num_parts, nsplit, gram, float(l1),
-                   float(l2), perms, perm_stride, perm_offset, S32, T32, viol_part, gram_partials, gram_out, ctrl,
+                   float(l2), perms, perm_stride, perm_offset, S32, T32, TC32, viol_part, gram_partials, gram_out, ctrl,
                    self._s())
 
     def shadows(self, F64, ld, rows, k, kp, S32, T32):

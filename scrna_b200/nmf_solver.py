@@ -21,6 +21,7 @@ Nothing here computes on the CPU: every array op is a C-ABI kernel; the host onl
 polls the 64-byte control block and (MU) applies the every-10-iterations stop rule to a scalar.
 """
 import math
+import os
 
 import numpy as np
 
@@ -31,9 +32,13 @@ def round_up(a, m):
     return ((int(a) + m - 1) // m) * m
 
 
-def pad_k(k):
+def pad_k(k, tensor_cores=False):
+    """Padded component count: a multiple of 4 (8 above 32) for the FP32-pipe sweeps, a multiple of 16 for
+    the tcgen05 sweep (the MMA's N)."""
     if k < 1 or k > _lib.MAX_K:
         raise ValueError("number of components must be in [1, %d], got %d" % (_lib.MAX_K, k))
+    if tensor_cores:
+        return round_up(k, 16)
     kp = round_up(k, 4)
     if kp > 32:
         kp = round_up(k, 8)
@@ -52,7 +57,8 @@ class DeviceMatrix:
     """X shard: genes x cells, row-major fp32 on the device, leading dimension padded to 32 cells
     (128 B) and zero-filled beyond the real cells."""
 
-    def __init__(self, data, n):
+    def __init__(self, data, n, tf32_exact=None):
+        self.tf32_exact = tf32_exact   # every element representable in TF32 (raw counts < 2048): lazily probed
         self.data = data
         self.g = int(data.shape[0])
         self.ldx = int(data.shape[1])
@@ -94,7 +100,12 @@ class DeviceMatrix:
         out = torch.zeros((max(self.n, 1), ldg), dtype=torch.float32, device=self.data.device)
         if self.n > 0:
             kernels.transpose(self.data, self.ldx, self.g, self.n, out, ldg)
-        return DeviceMatrix(out, self.g)
+        return DeviceMatrix(out, self.g, self.tf32_exact)
+
+    def is_tf32_exact(self, kernels):
+        if self.tf32_exact is None:
+            self.tf32_exact = bool(kernels.tf32_exact(self.data))
+        return self.tf32_exact
 
 
 class TorchDistComm:
@@ -129,7 +140,9 @@ class NmfSolver:
     fp32 row-major shadows Gs32 (g x kp) / Cs32 (n x kp) that the sweeps broadcast from shared
     memory, and the component-major fp32 shadow Ct32 for the residual kernel."""
 
-    def __init__(self, X, k, kernels=None, comm=None, transpose_copy=True):
+    def __init__(self, X, k, kernels=None, comm=None, transpose_copy=True, tensor_cores="auto"):
+        """tensor_cores: 'auto' = the tcgen05 sweep for k > 8 (where the FP32 pipe falls behind HBM) and, when
+        X is TF32-exact (raw counts), also for k <= 8; True / False force the choice."""
         if kernels is None:
             from .kernels import default_kernels
             kernels = default_kernels()
@@ -137,7 +150,24 @@ class NmfSolver:
         self.torch = kernels.torch
         self.X = X
         self.k = int(k)
-        self.kp = pad_k(self.k)
+        env = os.environ.get("SCRNA_B200_TC", "")   # "0" / "1" override the automatic choice (tests, A/B timing)
+        if env in ("0", "1") and tensor_cores == "auto":
+            tensor_cores = env == "1"
+        can_tc = bool(transpose_copy) and getattr(kernels, "tc_supported", lambda kp: False)(pad_k(self.k, True))
+        exact = False
+        if can_tc and tensor_cores:
+            # the shards must agree on the padded rank (it sizes the all-reduce payload): exact only if all are
+            inexact = kernels.torch.tensor([0.0 if X.is_tf32_exact(kernels) else 1.0], dtype=kernels.torch.float64,
+                                           device=X.data.device)
+            if comm is not None and comm.world > 1:
+                comm.all_reduce(inexact)
+            exact = float(inexact.item()) == 0.0
+        if tensor_cores == "auto":
+            self.tc = can_tc and (self.k > 8 or exact)
+        else:
+            self.tc = bool(tensor_cores) and can_tc
+        self.kp = pad_k(self.k, self.tc)
+        self.tc_flags = 32 if (self.tc and exact) else 0
         self.comm = comm if (comm is not None and comm.world > 1) else None
         t = self.torch
         dev = X.data.device
@@ -152,13 +182,22 @@ class NmfSolver:
         self.C64 = t.zeros((kp, ldn), dtype=f64, device=dev)
         self.Cs32 = t.zeros((n, kp), dtype=f32, device=dev)
         self.Ct32 = t.zeros((kp, ldn), dtype=f32, device=dev)
-        if self.XT is not None:
+        if self.tc:
+            self.Gtc = t.zeros(kernels.tc_shadow_elems(g, kp), dtype=f32, device=dev)
+            self.Ctc = t.zeros(kernels.tc_shadow_elems(n, kp), dtype=f32, device=dev)
+            self.SA = kernels.wtx_tc_splits(n, self.gcols, kp)
+            self.PA = t.zeros((self.SA, kp, ldg), dtype=f32, device=dev)
+            self.SB = kernels.wtx_tc_splits(g, X.ncols, kp)
+        elif self.XT is not None:
+            self.Gtc = self.Ctc = None
             self.SA = kernels.wtx_splits(n, self.gcols, kp)
             self.PA = t.zeros((self.SA, kp, ldg), dtype=f32, device=dev)
+            self.SB = kernels.wtx_splits(g, X.ncols, kp)
         else:
+            self.Gtc = self.Ctc = None
             self.SA = kernels.xht_splits(g, X.ncols, kp)
             self.PA = t.zeros((self.SA, g, kp), dtype=f32, device=dev)
-        self.SB = kernels.wtx_splits(g, X.ncols, kp)
+            self.SB = kernels.wtx_splits(g, X.ncols, kp)
         self.PB = t.zeros((self.SB, kp, ldn), dtype=f32, device=dev)
         # all-reduce payload: [ (X.C^T)^T (kp*ldg) | C.C^T (kp*kp) | 4 scalars ]
         self.R = t.zeros(kp * ldg + kp * kp + 4, dtype=f64, device=dev)
@@ -196,6 +235,9 @@ class NmfSolver:
         self.C64[:k, : X.n].copy_(t.from_numpy(C0).to(dev))
         self.kn.shadows(self.G64, self.ldg, X.g, k, kp, self.Gs32, None)
         self.kn.shadows(self.C64, self.ldn, max(X.n, 1), k, kp, self.Cs32, self.Ct32)
+        if self.tc:
+            self.kn.tc_shadow(self.G64, self.ldg, X.g, k, kp, self.Gtc)
+            self.kn.tc_shadow(self.C64, self.ldn, max(X.n, 1), k, kp, self.Ctc)
 
     def read_ctrl(self):
         raw = self.ctrl.cpu().numpy()
@@ -224,7 +266,11 @@ class NmfSolver:
         kn, X, kp = self.kn, self.X, self.kp
         if self.XT is not None:
             XT = self.XT
-            kn.wtx_partial(XT.data, XT.ldx, XT.g, self.gcols, self.Cs32, kp, self.PA, self.ldg, self.SA, ctrl)
+            if self.tc:
+                kn.wtx_partial_tc(XT.data, XT.ldx, XT.g, self.gcols, self.Ctc, kp, self.PA, self.ldg, self.SA, ctrl,
+                                  flags=self.tc_flags)
+            else:
+                kn.wtx_partial(XT.data, XT.ldx, XT.g, self.gcols, self.Cs32, kp, self.PA, self.ldg, self.SA, ctrl)
             if self._g_num_from_R:
                 kn.reduce_cols(self.PA, self.SA, kp, self.ldg, self.gcols, self.R_xht, ctrl)
         else:
@@ -243,20 +289,25 @@ class NmfSolver:
                        None if fused else self.R_xht, self.R_cct, l1, l2, self.perms, stride, offset,
                        self.Gs32, None, self.violG, ctrl,
                        num_parts=self.PA if fused else None, nsplit=self.SA if fused else 0,
-                       gram_partials=self.gpartG, gram_out=self.gtg)
+                       gram_partials=self.gpartG, gram_out=self.gtg, TC32=self.Gtc)
 
     def _half_C(self, solver, l1, l2, stride, offset, ctrl):
         kn, X, kp = self.kn, self.X, self.kp
-        kn.wtx_partial(X.data, X.ldx, X.g, X.ncols, self.Gs32, kp, self.PB, self.ldn, self.SB, ctrl)
+        if self.tc:
+            kn.wtx_partial_tc(X.data, X.ldx, X.g, X.ncols, self.Gtc, kp, self.PB, self.ldn, self.SB, ctrl,
+                              flags=self.tc_flags)
+        else:
+            kn.wtx_partial(X.data, X.ldx, X.g, X.ncols, self.Gs32, kp, self.PB, self.ldn, self.SB, ctrl)
         if self.fuse_reduce:
             kn.update(solver, self.C64, self.ldn, max(X.n, 1), self.k, kp, None, self.gtg, l1, l2,
                       self.perms, stride, offset, self.Cs32, self.Ct32, self.violC, ctrl,
-                      num_parts=self.PB, nsplit=self.SB, gram_partials=self.gpartC, gram_out=self.R_cct)
+                      num_parts=self.PB, nsplit=self.SB, gram_partials=self.gpartC, gram_out=self.R_cct,
+                      TC32=self.Ctc)
         else:
             kn.reduce_cols(self.PB, self.SB, kp, self.ldn, X.ncols, self.NB, ctrl)
             kn.update(solver, self.C64, self.ldn, max(X.n, 1), self.k, kp, self.NB, self.gtg, l1, l2,
                       self.perms, stride, offset, self.Cs32, self.Ct32, self.violC, ctrl,
-                      gram_partials=self.gpartC, gram_out=self.R_cct)
+                      gram_partials=self.gpartC, gram_out=self.R_cct, TC32=self.Ctc)
 
     def frobenius_error(self):
         """||X - G.C||_F over all shards (sklearn _beta_divergence(..., square_root=True))."""

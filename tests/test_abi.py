@@ -15,7 +15,7 @@ HEADER = os.path.join(ROOT, "include", "scrna_b200.h")
 def declared_symbols():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\bint\s+(scrna_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\bint(?:64_t)?\s+(scrna_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_declares_functions():

@@ -21,9 +21,84 @@ def _recon_err(X, W, H):
     return np.linalg.norm(X - W @ H) / np.linalg.norm(X)
 
 
-def _solver(kernels, X, k, transpose_copy=True):
+def _solver(kernels, X, k, transpose_copy=True, tensor_cores="auto"):
     from scrna_b200.nmf_solver import DeviceMatrix, NmfSolver
-    return NmfSolver(DeviceMatrix.from_host(X, kernels), k, kernels=kernels, transpose_copy=transpose_copy)
+    return NmfSolver(DeviceMatrix.from_host(X, kernels), k, kernels=kernels, transpose_copy=transpose_copy,
+                     tensor_cores=tensor_cores)
+
+
+@pytest.fixture(params=["simt", "tcgen05"])
+def sweep_path(request, monkeypatch):
+    """Runs a test once on the FP32-pipe sweeps and once on the tcgen05 sweep (SCRNA_B200_TC override of the
+    solver's automatic choice; the classes construct their solver internally)."""
+    monkeypatch.setenv("SCRNA_B200_TC", "1" if request.param == "tcgen05" else "0")
+    return request.param
+
+
+@pytest.mark.parametrize("exact_x", [True, False])
+@pytest.mark.parametrize("g,n,k", [(1000, 1000, 8), (333, 517, 7), (64, 4100, 5), (2500, 130, 16), (129, 257, 33),
+                                   (40, 36, 3), (700, 900, 50), (5, 7, 2), (3000, 2000, 64), (1037, 1500, 17)])
+def test_tcgen05_sweeps_match_fp64_products(kernels, g, n, k, exact_x):
+    """The tensor-core sweep (3xTF32 split, TMEM accumulators drained every 512 rows) on both resident copies
+    of X, against fp64 products; counts (TF32-exact, single X pass) and wide-dynamic-range reals."""
+    torch = kernels.torch
+    rng = np.random.RandomState(g + 3 * n + k)
+    if exact_x:
+        X = rng.poisson(2.0, size=(g, n)).astype(np.float64)
+    else:
+        X = rng.rand(g, n) * np.exp(2.0 * rng.randn(g, n))
+    G = np.abs(rng.randn(g, k)) + 0.01
+    C = np.abs(rng.randn(k, n)) + 0.01
+    slv = _solver(kernels, X, k, tensor_cores=True)
+    assert slv.tc and slv.kp % 16 == 0 and (slv.tc_flags == 32) == exact_x
+    slv._load_factors(G, C)
+    slv._g_num_from_R = True
+    slv._products_for_G(None, with_gram=True)
+    torch.cuda.synchronize()
+    X32 = X.astype(np.float32).astype(np.float64)
+    xht = slv.R_xht.view(slv.kp, slv.ldg)[:k, :g].cpu().numpy().T
+    assert rel_fro(xht, X32 @ C.T) < 1e-5
+    assert np.all(slv.R_xht.view(slv.kp, slv.ldg)[k:, :g].cpu().numpy() == 0)
+    kernels.wtx_partial_tc(slv.X.data, slv.X.ldx, g, slv.X.ncols, slv.Gtc, slv.kp, slv.PB, slv.ldn, slv.SB, None,
+                           flags=slv.tc_flags)
+    kernels.reduce_cols(slv.PB, slv.SB, slv.kp, slv.ldn, slv.X.ncols, slv.NB, None)
+    torch.cuda.synchronize()
+    wtx = slv.NB[:k, :n].cpu().numpy()
+    assert rel_fro(wtx, G.T @ X32) < 1e-5
+    assert np.all(slv.NB[k:, :n].cpu().numpy() == 0)
+    # elementwise: no column/row of the tile mapping is misplaced
+    ref = G.T @ X32
+    assert np.max(np.abs(wtx - ref) / (np.abs(ref) + 1e-3 * np.abs(ref).max())) < 1e-4
+
+
+def test_update_writes_tcgen05_operand_shadow(kernels):
+    """The epilogue's [hi | lo] operand shadow equals the one scrna_nmf_tc_shadow builds from the master."""
+    import scrna_b200._lib as L
+    torch = kernels.torch
+    rng = np.random.RandomState(5)
+    rows, k, kp, ld = 1001, 13, 16, 1024
+    dev = torch.device("cuda")
+    F = np.zeros((kp, ld)); F[:k, :rows] = np.abs(rng.randn(k, rows))
+    F64 = torch.from_numpy(F).to(dev)
+    N = np.zeros((kp, ld)); N[:k, :rows] = np.abs(rng.randn(k, rows)) * 10
+    A = np.abs(rng.randn(40, k)); Gm = np.zeros((kp, kp)); Gm[:k, :k] = A.T @ A
+    n_el = kernels.tc_shadow_elems(rows, kp)
+    tc_a = torch.zeros(n_el, dtype=torch.float32, device=dev)
+    tc_b = torch.full((n_el,), -1.0, dtype=torch.float32, device=dev)
+    S32 = torch.zeros((rows, kp), dtype=torch.float32, device=dev)
+    viol = torch.zeros(kernels.update_blocks(rows), dtype=torch.float64, device=dev)
+    ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
+    kernels.update(L.SOLVER_MU, F64, ld, rows, k, kp, torch.from_numpy(N).to(dev), torch.from_numpy(Gm).to(dev), 0.5, 0.1,
+                   None, 1, 0, S32, None, viol, ctrl, TC32=tc_a)
+    kernels.tc_shadow(F64, ld, rows, k, kp, tc_b)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(tc_a.cpu().numpy(), tc_b.cpu().numpy())
+    sh = tc_b.cpu().numpy().reshape(-1, 2 * kp, 4)          # [(r/4)][n][r%4]
+    got = F64.cpu().numpy()[:k, :rows]
+    hi = sh[:, :kp, :].transpose(1, 0, 2).reshape(kp, -1)[:k, :rows].astype(np.float64)
+    lo = sh[:, kp:, :].transpose(1, 0, 2).reshape(kp, -1)[:k, :rows].astype(np.float64)
+    assert np.max(np.abs(hi + lo - got) / got.max()) < 2.0 ** -20
+    assert np.all((hi.astype(np.float32).view(np.uint32) & 0x1fff) == 0)
 
 
 @pytest.mark.parametrize("transpose_copy", [True, False])
@@ -35,7 +110,7 @@ def test_sweeps_match_fp64_products(kernels, g, n, k, transpose_copy):
     X = rng.poisson(2.0, size=(g, n)).astype(np.float64)
     G = np.abs(rng.randn(g, k))
     C = np.abs(rng.randn(k, n))
-    slv = _solver(kernels, X, k, transpose_copy)
+    slv = _solver(kernels, X, k, transpose_copy, tensor_cores=False)
     slv._load_factors(G, C)
     if transpose_copy:
         np.testing.assert_array_equal(slv.XT.data[:n, :g].cpu().numpy(), X.T.astype(np.float32))
@@ -126,7 +201,7 @@ def test_single_update_matches_oracle(kernels, solver, fused_parts):
     np.testing.assert_array_equal(T32.cpu().numpy()[:k, :rows].T, got.astype(np.float32))
 
 
-def test_nmf_clustering_default_data_vs_reference_golden(kernels, default_sim, golden):
+def test_nmf_clustering_default_data_vs_reference_golden(kernels, default_sim, golden, sweep_path):
     from scrna_b200 import NmfClustering
     g = golden("nmf_source")
     nmf = NmfClustering(default_sim["src"], default_sim["gene_ids"], 8, default_sim["src_labels"])
@@ -141,7 +216,7 @@ def test_nmf_clustering_default_data_vs_reference_golden(kernels, default_sim, g
     np.testing.assert_array_equal(nmf.cluster_labels, g["nmf_labels"])
 
 
-def test_initw_default_data_vs_reference_golden(kernels, default_sim, golden):
+def test_initw_default_data_vs_reference_golden(kernels, default_sim, golden, sweep_path):
     from scrna_b200 import NmfClustering_initW
     g = golden("nmf_source")
     nmf = NmfClustering_initW(default_sim["src"], default_sim["gene_ids"], 7, default_sim["src_labels"])
@@ -152,7 +227,7 @@ def test_initw_default_data_vs_reference_golden(kernels, default_sim, golden):
     np.testing.assert_array_equal(nmf.cluster_labels, g["initw_labels"])
 
 
-def test_mu_solver_vs_sklearn_golden(kernels, default_sim, golden):
+def test_mu_solver_vs_sklearn_golden(kernels, default_sim, golden, sweep_path):
     g = golden("nmf_source")
     slv = _solver(kernels, default_sim["src"], 8)
     res = slv.fit(g["W0"], g["H0"], solver="mu", l1_G=7.5, l2_G=2.5, l1_C=7.5, l2_C=2.5, tol=1e-4, max_iter=200)
@@ -166,7 +241,7 @@ def test_mu_solver_vs_sklearn_golden(kernels, default_sim, golden):
 
 @pytest.mark.parametrize("g,n,k,solver", [(300, 220, 5, "cd"), (257, 1030, 12, "cd"), (300, 220, 5, "mu"),
                                           (120, 333, 20, "mu"), (90, 75, 3, "cd")])
-def test_fit_vs_oracle_seeded(kernels, g, n, k, solver):
+def test_fit_vs_oracle_seeded(kernels, g, n, k, solver, sweep_path):
     rng = np.random.RandomState(g * 7 + n)
     mu = rng.gamma(2.0, 1.0, size=(g, 1)) * (1 + (rng.rand(g, 6) < 0.2) @ (rng.rand(6, n) < 0.3) * 3.0)
     X = rng.poisson(mu).astype(np.float64)

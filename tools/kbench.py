@@ -37,7 +37,10 @@ def main():
     ap.add_argument("--sa", type=int, nargs="*", default=[])
     ap.add_argument("--sb", type=int, nargs="*", default=[])
     ap.add_argument("--lowmem", action="store_true")
-    ap.add_argument("--variants", type=int, nargs="*", default=[0])
+    ap.add_argument("--variants", type=int, nargs="*", default=[2])
+    ap.add_argument("--tc", default="auto", help="auto | 0 | 1: tcgen05 sweep choice passed to NmfSolver")
+    ap.add_argument("--real", action="store_true", help="non-integer X (general 3xTF32 path, Xl pass on)")
+    ap.add_argument("--out", default="gpurun_out/kbench.json")
     args = ap.parse_args()
     kn = default_kernels()
     g, n = args.genes, args.cells
@@ -50,17 +53,33 @@ def main():
         r1 = min(g, r0 + rows)
         lam = torch.rand((r1 - r0, 1), device=dev, generator=gen) * 4
         X[r0:r1, :n] = torch.poisson(lam.expand(r1 - r0, n), generator=gen)
+        if args.real:
+            X[r0:r1, :n] = torch.log2(X[r0:r1, :n] + 1.0)
     dm = DeviceMatrix(X, n)
     bytes_x = g * ldx * 4
     out = []
     for k in args.k:
-        slv = NmfSolver(dm, k, kernels=kn)
+        tc = {"auto": "auto", "0": False, "1": True}[args.tc]
+        slv = NmfSolver(dm, k, kernels=kn, tensor_cores=tc)
         rng = np.random.RandomState(0)
         G0 = np.abs(rng.randn(g, k)); C0 = np.abs(rng.randn(k, n))
         slv._load_factors(G0, C0)
         kp = slv.kp
         sa_list = args.sa or [slv.SA]
         sb_list = args.sb or [slv.SB]
+        if slv.tc:
+            med, best = timeit(lambda: kn.wtx_partial_tc(X, ldx, g, dm.ncols, slv.Gtc, kp, slv.PB, slv.ldn, slv.SB, None,
+                                                         flags=slv.tc_flags))
+            out.append(dict(kernel="sweep_X(tcgen05)", k=k, kp=kp, exact=slv.tc_flags == 32, nsplit=slv.SB, ms=med,
+                            best_ms=best, gbs=bytes_x / med / 1e6))
+            print(out[-1], flush=True)
+            XT = slv.XT
+            med, best = timeit(lambda: kn.wtx_partial_tc(XT.data, XT.ldx, XT.g, slv.gcols, slv.Ctc, kp, slv.PA, slv.ldg,
+                                                         slv.SA, None, flags=slv.tc_flags))
+            out.append(dict(kernel="sweep_XT(tcgen05)", k=k, kp=kp, exact=slv.tc_flags == 32, nsplit=slv.SA, ms=med,
+                            best_ms=best, gbs=XT.g * XT.ldx * 4 / med / 1e6))
+            print(out[-1], flush=True)
+            sb_list, sa_list = [], []
         for sb in sb_list:
           for var in args.variants:
             PB = torch.zeros((sb, kp, slv.ldn), dtype=torch.float32, device=dev)
@@ -102,11 +121,11 @@ def main():
                 slv._half_C(code, 7.5, 2.5, 0, 0, None)
             med, best = timeit(it, warm=3, reps=10)
             algo = 2 * bytes_x + 2 * (g + n) * k * 4
-            out.append(dict(kernel="iteration_" + solver, k=k, ms=med, best_ms=best, it_per_s=1000.0 / med,
+            out.append(dict(kernel="iteration_" + solver, k=k, kp=kp, tc=bool(slv.tc), ms=med, best_ms=best, it_per_s=1000.0 / med,
                             gbs=algo / med / 1e6))
             print(out[-1], flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/kbench.json", "w") as f:
+    with open(args.out, "w") as f:
         json.dump(out, f, indent=1)
 
 
