@@ -28,6 +28,9 @@ import numpy as np  # noqa: E402
 GENES, CELLS, K = 20000, 100000, 8
 L1, L2 = 7.5, 2.5                      # alpha=10, l1_ratio=.75 (cmd_source.py:34-35)
 METRIC = "NMF MU iters/s (20k genes x 100k cells, k=8)"
+# dram__bytes_read.sum + dram__bytes_write.sum per sweep launch from the committed `ncu --set full` captures of
+# the default workload on one GPU (profiles/r01_sweep_full_raw.csv, profiles/r01_tcgen05_sweep_k32_full_raw.csv)
+NCU_TRAFFIC = {"simt": 8.003e9 + 0.03e9, "tcgen05": 8.033e9 + 0.023e9}
 UNIT = "iterations/s"
 E2E_ITERS = 100                        # NmfClustering.apply default max_iter (nmf_clustering.py:20)
 CPU_SAMPLE_CELLS = 10000
@@ -272,8 +275,13 @@ def run_gpu(args):
     avg_ms = sum(sweep_ms) / len(sweep_ms)
     achieved = (sum(sweep_bytes) / len(sweep_bytes)) / (avg_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
+    traffic = args.traffic
+    if traffic is None and world == 1 and (genes, cells) == (GENES, CELLS):
+        traffic = NCU_TRAFFIC["tcgen05" if slv.tc else "simt"]
+    kname = ("wtx_tc_kernel<KP=%d> (tcgen05.mma kind::tf32%s)" % (slv.kp, ", TF32-exact X" if slv.tc_flags else "")
+             if slv.tc else "wtx_partial_kernel<KP=%d>" % slv.kp)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": args.traffic, "kernel": "wtx_partial_kernel<KP=%d>" % slv.kp, "peak_source": peak_src,
+                "traffic": traffic, "kernel": kname, "peak_source": peak_src,
                 "launch_ms": avg_ms, "launches_timed": len(sweep_ms),
                 "sweep_share_of_step": sum(sweep_ms) / ms,
                 "algorithmic_bytes_per_launch": sum(sweep_bytes) / len(sweep_bytes),
@@ -289,6 +297,7 @@ def run_gpu(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    slv_tc, slv_kp = bool(slv.tc), slv.kp
     Xh = torch.empty((genes, n_loc), dtype=torch.float32).pin_memory()
     Xh.copy_(Xd[:, :n_loc])
     del slv, dm, Xd
@@ -336,13 +345,14 @@ def run_gpu(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "metric": METRIC if k == K else METRIC.replace("k=8", "k=%d" % k), "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "NMF MU 20000 genes x 100000 cells k=8, cells sharded over the GPUs "
-                                   "(BASELINE.json configs[2])",
+            "config": {"workload": "NMF MU %d genes x %d cells k=%d, cells sharded over the GPUs "
+                                   "(BASELINE.json configs[2])" % (genes, cells, k),
                        "genes": genes, "cells": cells, "k": k, "solver": "mu", "l1": L1, "l2": L2,
                        "x_storage": "fp32 genes x cells + resident transposed copy",
+                       "sweep": "tcgen05 3xTF32 (kp=%d)" % slv_kp if slv_tc else "fp32 FMA (kp=%d)" % slv_kp,
                        "l2_flush": "none needed: each sweep streams %.1f GB per GPU, far larger than the 126 MB L2"
                                    % (genes * n_loc * 4 / 1e9),
                        "parallelism": "cells sharded x%d, one all-reduce of %d fp64 per iteration"

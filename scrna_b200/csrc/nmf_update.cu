@@ -9,6 +9,7 @@
 namespace scrna {
 
 constexpr int UPD_THREADS = 128;
+constexpr int UPD_LD = UPD_THREADS + 1;  // smem row pitch (doubles): column reads of the Gram epilogue stay conflict-free
 
 // ---- fixed-order reduction of the sweep partials ---------------------------------------------
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int nsplit, int64_t count,
@@ -126,8 +127,8 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
   if (ctrl_done(ctrl)) return;
   extern __shared__ double smem[];
   double* sg = smem;                         // kp*kp Gram
-  double* sw = sg + kp * kp;                 // k * UPD_THREADS factor entries
-  double* sn = sw + (size_t)k * UPD_THREADS; // k * UPD_THREADS numerators
+  double* sw = sg + kp * kp;             // k x UPD_LD factor entries
+  double* sn = sw + (size_t)k * UPD_LD;  // k x UPD_LD numerators
   __shared__ double scratch[32];
   __shared__ int sperm[SCRNA_MAX_K];
   __shared__ int snan;
@@ -146,7 +147,7 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
   double viol = 0.0;
   bool nan_seen = false;
   if (live) {
-    for (int t = 0; t < k; ++t) sw[t * UPD_THREADS + tid] = F64[(int64_t)t * ld + r];
+    for (int t = 0; t < k; ++t) sw[t * UPD_LD + tid] = F64[(int64_t)t * ld + r];
     if (num_parts) {
       // fixed-order fp64 sum of the sweep's split partials (kp x ld fp32 each); eight components at a
       // time so that 8 x (unrolled splits) independent loads are in flight per thread
@@ -164,42 +165,58 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          if (t0 + u < k) sn[(t0 + u) * UPD_THREADS + tid] = a8[u];
+          if (t0 + u < k) sn[(t0 + u) * UPD_LD + tid] = a8[u];
       }
     } else {
-      for (int t = 0; t < k; ++t) sn[t * UPD_THREADS + tid] = num[(int64_t)t * ld + r];
+      for (int t = 0; t < k; ++t) sn[t * UPD_LD + tid] = num[(int64_t)t * ld + r];
     }
     if (SOLVER == SCRNA_SOLVER_MU) {
-      // W *= XHt / (W.HHt + l1 + l2*W); the denominator uses the OLD row throughout
-      for (int t = 0; t < k; ++t) {
-        double den = 0.0;
-        for (int q = 0; q < k; ++q) den += sw[q * UPD_THREADS + tid] * sg[q * kp + t];
-        const double w = sw[t * UPD_THREADS + tid];
-        if (l1 > 0.0) den += l1;
-        if (l2 > 0.0) den = den + l2 * w;
-        if (den == 0.0) den = (double)kEpsMU;
-        sn[t * UPD_THREADS + tid] = w * (sn[t * UPD_THREADS + tid] / den);  // numerator slot := new value
+      // W *= XHt / (W.HHt + l1 + l2*W); the denominator uses the OLD row throughout.  Eight components at
+      // a time: eight independent fp64 chains per thread, the Gram row broadcast from shared memory.
+      for (int t0 = 0; t0 < k; t0 += 8) {
+        double den[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) den[u] = 0.0;
+        for (int q = 0; q < k; ++q) {
+          const double wq = sw[q * UPD_LD + tid];
+          const double* gq = sg + q * kp + t0;  // kp is a multiple of 4 and the Gram is zero-padded to kp x kp
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (t0 + u < kp) den[u] += wq * gq[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int t = t0 + u;
+          if (t < k) {
+            const double w = sw[t * UPD_LD + tid];
+            double d = den[u];
+            if (l1 > 0.0) d += l1;
+            if (l2 > 0.0) d = d + l2 * w;
+            if (d == 0.0) d = (double)kEpsMU;
+            sn[t * UPD_LD + tid] = w * (sn[t * UPD_LD + tid] / d);  // numerator slot := new value
+          }
+        }
       }
-      for (int t = 0; t < k; ++t) sw[t * UPD_THREADS + tid] = sn[t * UPD_THREADS + tid];
+      for (int t = 0; t < k; ++t) sw[t * UPD_LD + tid] = sn[t * UPD_LD + tid];
     } else {
       // _update_cdnmf_fast with HHt.diag += l2 and XHt -= l1 (_nmf.py:383-388)
       for (int s = 0; s < k; ++s) {
         const int t = sperm[s];
-        double grad = -(sn[t * UPD_THREADS + tid] - l1);
+        double grad = -(sn[t * UPD_LD + tid] - l1);
         for (int q = 0; q < k; ++q) {
           double h = sg[t * kp + q];
           if (q == t) h += l2;
-          grad += h * sw[q * UPD_THREADS + tid];
+          grad += h * sw[q * UPD_LD + tid];
         }
-        const double w = sw[t * UPD_THREADS + tid];
+        const double w = sw[t * UPD_LD + tid];
         const double pg = (w == 0.0) ? fmin(0.0, grad) : grad;
         viol += fabs(pg);
         const double hess = sg[t * kp + t] + l2;
-        if (hess != 0.0) sw[t * UPD_THREADS + tid] = fmax(w - grad / hess, 0.0);
+        if (hess != 0.0) sw[t * UPD_LD + tid] = fmax(w - grad / hess, 0.0);
       }
     }
     for (int t = 0; t < k; ++t) {
-      const double v = sw[t * UPD_THREADS + tid];
+      const double v = sw[t * UPD_LD + tid];
       nan_seen |= (v != v);
       const int64_t e = (int64_t)t * ld + r;
       F64[e] = v;
@@ -209,7 +226,7 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
       // [hi | lo] TF32 operand shadow of the tensor-core sweep (nmf_sweep_tc.cu): [(r/4)][n < 2kp][r%4]
       float* base = TC32 + ((r >> 2) * 2 * kp) * 4 + (r & 3);
       for (int t = 0; t < k; ++t) {
-        const double v = sw[t * UPD_THREADS + tid];
+        const double v = sw[t * UPD_LD + tid];
         const float h = __uint_as_float(__float_as_uint((float)v) & 0xffffe000u);
         base[t * 4] = h;
         base[(kp + t) * 4] = __uint_as_float(__float_as_uint((float)(v - (double)h)) & 0xffffe000u);
@@ -219,17 +236,17 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
       float* srow = S32 + r * kp;
       for (int t = 0; t < kp; t += 4) {
         float4 o;
-        o.x = (t + 0 < k) ? (float)sw[(t + 0) * UPD_THREADS + tid] : 0.f;
-        o.y = (t + 1 < k) ? (float)sw[(t + 1) * UPD_THREADS + tid] : 0.f;
-        o.z = (t + 2 < k) ? (float)sw[(t + 2) * UPD_THREADS + tid] : 0.f;
-        o.w = (t + 3 < k) ? (float)sw[(t + 3) * UPD_THREADS + tid] : 0.f;
+        o.x = (t + 0 < k) ? (float)sw[(t + 0) * UPD_LD + tid] : 0.f;
+        o.y = (t + 1 < k) ? (float)sw[(t + 1) * UPD_LD + tid] : 0.f;
+        o.z = (t + 2 < k) ? (float)sw[(t + 2) * UPD_LD + tid] : 0.f;
+        o.w = (t + 3 < k) ? (float)sw[(t + 3) * UPD_LD + tid] : 0.f;
         *reinterpret_cast<float4*>(srow + t) = o;
       }
     }
   }
   if (nan_seen) snan = 1;
   if (gram_part_out && !live)
-    for (int t = 0; t < k; ++t) sw[t * UPD_THREADS + tid] = 0.0;
+    for (int t = 0; t < k; ++t) sw[t * UPD_LD + tid] = 0.0;
   const double bsum = block_sum(viol, scratch);  // contains __syncthreads
   if (tid == 0) {
     if (viol_part) viol_part[blockIdx.x] = bsum;
@@ -237,16 +254,26 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
   }
   if (gram_part_out) {
     // Gram of this block's NEW rows: the next half step needs F^T F (K4 fused into the epilogue)
+    // upper triangle only (mirrored), four independent chains over the block's rows
     double* gp = gram_part_out + (int64_t)blockIdx.x * kp * kp;
     for (int o = tid; o < kp * kp; o += UPD_THREADS) {
       const int a = o / kp, b = o - a * kp;
-      double acc = 0.0;
-      if (a < k && b < k) {
-        const double* ra = sw + a * UPD_THREADS;
-        const double* rb = sw + b * UPD_THREADS;
-        for (int q = 0; q < UPD_THREADS; ++q) acc = fma(ra[q], rb[q], acc);
+      if (a >= k || b >= k) {
+        gp[o] = 0.0;
+      } else if (a <= b) {
+        const double* ra = sw + a * UPD_LD;
+        const double* rb = sw + b * UPD_LD;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int q = 0; q < UPD_THREADS; q += 4) {
+          a0 = fma(ra[q], rb[q], a0);
+          a1 = fma(ra[q + 1], rb[q + 1], a1);
+          a2 = fma(ra[q + 2], rb[q + 2], a2);
+          a3 = fma(ra[q + 3], rb[q + 3], a3);
+        }
+        const double acc = (a0 + a1) + (a2 + a3);
+        gp[o] = acc;
+        gp[b * kp + a] = acc;
       }
-      gp[o] = acc;
     }
   }
 }
@@ -404,7 +431,7 @@ extern "C" int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t row
   if (!F64 || (!num && !num_parts) || (num_parts && nsplit <= 0) || !gram || rows <= 0 || ld < rows || k <= 0 ||
       k > kp || kp > SCRNA_MAX_K || (kp & 3) || (gram_out && !gram_partials))
     return SCRNA_ERR_BADARG;
-  const size_t smem = ((size_t)kp * kp + 2 * (size_t)k * UPD_THREADS) * sizeof(double);
+  const size_t smem = ((size_t)kp * kp + 2 * (size_t)k * UPD_LD) * sizeof(double);
   const int nblk = (int)ceil_div(rows, UPD_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
