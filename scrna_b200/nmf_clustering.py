@@ -46,12 +46,33 @@ def _check_nan(W, H, alpha, k, l1, X):
             alpha, k, l1, X.shape[0], X.shape[1]))
 
 
+DEVICE_INIT_MIN_ELEMENTS = 1 << 24   # below this the host routine costs milliseconds and is bit-faithful
+
+
 def _fit_nmf(X, k, alpha, l1, max_iter, tol, solver, init, comm=None):
-    """decomp.NMF(init='nndsvdar', solver='cd', shuffle=True, random_state=0).fit_transform(X)."""
-    W0, H0 = nndsvdar_init(X, k) if init is None else init
+    """decomp.NMF(init='nndsvdar', solver='cd', shuffle=True, random_state=0).fit_transform(X).
+
+    init: (W0, H0) | 'host' (sklearn's routine on the host, bit-identical to the reference's start) |
+    'device' (same algorithm and RNG stream with every pass over X on the GPU, scrna_b200/nmf_init.py) |
+    None = 'device' for matrices of at least 2^24 elements (where the host passes cost seconds to minutes)
+    on a single GPU with k <= 54, else 'host'."""
     l1r, l2r = _regularization(alpha, l1)
     dm = DeviceMatrix.from_host(X, _kernels())
-    slv = NmfSolver(dm, k, comm=comm)
+    XT = None
+    if init is None:
+        big = X.shape[0] * X.shape[1] >= DEVICE_INIT_MIN_ELEMENTS
+        init = 'device' if (big and comm is None and k <= 54) else 'host'
+    if isinstance(init, str):
+        if init == 'device':
+            from .nmf_init import nndsvdar_init_device
+            W0, H0, XT = nndsvdar_init_device(dm, k, _kernels(), seed=0)
+        elif init == 'host':
+            W0, H0 = nndsvdar_init(X, k)
+        else:
+            raise ValueError("init must be (W0, H0), 'host' or 'device'")
+    else:
+        W0, H0 = init
+    slv = NmfSolver(dm, k, comm=comm, XT=XT)
     res = slv.fit(W0, H0, solver=solver, l1_G=l1r, l2_G=l2r, l1_C=l1r, l2_C=l2r, tol=tol,
                   max_iter=max_iter, first="G", seed=0, shuffle=True)
     return res

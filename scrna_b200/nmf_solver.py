@@ -140,7 +140,7 @@ class NmfSolver:
     fp32 row-major shadows Gs32 (g x kp) / Cs32 (n x kp) that the sweeps broadcast from shared
     memory, and the component-major fp32 shadow Ct32 for the residual kernel."""
 
-    def __init__(self, X, k, kernels=None, comm=None, transpose_copy=True, tensor_cores="auto"):
+    def __init__(self, X, k, kernels=None, comm=None, transpose_copy=True, tensor_cores="auto", XT=None):
         """tensor_cores: 'auto' = the tcgen05 sweep for k > 8 (where the FP32 pipe falls behind HBM) and, when
         X is TF32-exact (raw counts), also for k <= 8; True / False force the choice."""
         if kernels is None:
@@ -176,7 +176,10 @@ class NmfSolver:
         self.ldg = ldg = round_up(g, 32)
         self.gcols = round_up(g, 4)
         f64, f32 = t.float64, t.float32
-        self.XT = X.transposed(kernels) if transpose_copy else None
+        if XT is not None and transpose_copy:
+            self.XT = XT          # a resident transposed copy built by another solver on the same X
+        else:
+            self.XT = X.transposed(kernels) if transpose_copy else None
         self.G64 = t.zeros((kp, ldg), dtype=f64, device=dev)
         self.Gs32 = t.zeros((g, kp), dtype=f32, device=dev)
         self.C64 = t.zeros((kp, ldn), dtype=f64, device=dev)
@@ -221,23 +224,70 @@ class NmfSolver:
         self.perms = None
 
     # ---- helpers ------------------------------------------------------------------------------
-    def _load_factors(self, G0, C0):
+    def load_G(self, G0):
+        """Gene factor (g x k host array) -> fp64 master + the operand shadows of the sweeps."""
         t = self.torch
         X, k, kp = self.X, self.k, self.kp
         G0 = np.ascontiguousarray(np.asarray(G0, dtype=np.float64).T)
-        C0 = np.ascontiguousarray(C0, dtype=np.float64)
-        if G0.shape != (k, X.g) or C0.shape != (k, X.n):
+        if G0.shape != (k, X.g):
             raise ValueError("init shapes do not match X %dx%d, k=%d" % (X.g, X.n, k))
-        dev = X.data.device
         self.G64.zero_()
-        self.C64.zero_()
-        self.G64[:k, : X.g].copy_(t.from_numpy(G0).to(dev))
-        self.C64[:k, : X.n].copy_(t.from_numpy(C0).to(dev))
+        self.G64[:k, : X.g].copy_(t.from_numpy(G0).to(X.data.device))
         self.kn.shadows(self.G64, self.ldg, X.g, k, kp, self.Gs32, None)
-        self.kn.shadows(self.C64, self.ldn, max(X.n, 1), k, kp, self.Cs32, self.Ct32)
         if self.tc:
             self.kn.tc_shadow(self.G64, self.ldg, X.g, k, kp, self.Gtc)
+
+    def load_C(self, C0):
+        """Cell factor (k x n host array) -> fp64 master + shadows."""
+        t = self.torch
+        X, k, kp = self.X, self.k, self.kp
+        C0 = np.ascontiguousarray(C0, dtype=np.float64)
+        if C0.shape != (k, X.n):
+            raise ValueError("init shapes do not match X %dx%d, k=%d" % (X.g, X.n, k))
+        self.C64.zero_()
+        self.C64[:k, : X.n].copy_(t.from_numpy(C0).to(X.data.device))
+        self.kn.shadows(self.C64, self.ldn, max(X.n, 1), k, kp, self.Cs32, self.Ct32)
+        if self.tc:
             self.kn.tc_shadow(self.C64, self.ldn, max(X.n, 1), k, kp, self.Ctc)
+
+    def _load_factors(self, G0, C0):
+        self.load_G(G0)
+        self.load_C(C0)
+
+    # ---- skinny products with the resident X (device NNDSVD init, scrna_b200/nmf_init.py) -------------
+    def x_times(self, Q):
+        """X @ Q for a host (n x k) matrix Q of any sign: one sweep of the X^T copy.  Returns g x k fp64."""
+        self.load_C(np.asarray(Q).T)
+        keep = self._g_num_from_R
+        self._g_num_from_R = True
+        self._products_for_G(None)
+        self._g_num_from_R = keep
+        self._allreduce_R()
+        return np.ascontiguousarray(self.R_xht.view(self.kp, self.ldg)[: self.k, : self.X.g].cpu().numpy().T)
+
+    def xt_times(self, Q):
+        """X^T @ Q for a host (g x k) matrix Q: one sweep of X.  Returns this shard's n x k fp64."""
+        kn, X, kp = self.kn, self.X, self.kp
+        self.load_G(Q)
+        if self.tc:
+            kn.wtx_partial_tc(X.data, X.ldx, X.g, X.ncols, self.Gtc, kp, self.PB, self.ldn, self.SB, None,
+                              flags=self.tc_flags)
+        else:
+            kn.wtx_partial(X.data, X.ldx, X.g, X.ncols, self.Gs32, kp, self.PB, self.ldn, self.SB, None)
+        kn.reduce_cols(self.PB, self.SB, kp, self.ldn, X.ncols, self.NB, None)
+        return np.ascontiguousarray(self.NB[: self.k, : X.n].cpu().numpy().T)
+
+    def x_sum(self):
+        """sum_ij |X_ij| over this shard (= sum X for the non-negative NMF input): the residual kernel
+        against all-zero factors."""
+        X = self.X
+        self.Gs32.zero_()
+        self.Ct32.zero_()
+        self.kn.residual(X.data, X.ldx, X.g, X.ncols, self.Gs32, self.Ct32, self.ldn, self.kp, 1, self.res_part,
+                         self.res_out)
+        if self.comm is not None:
+            self.comm.all_reduce(self.res_out)
+        return float(self.res_out.cpu()[0])
 
     def read_ctrl(self):
         raw = self.ctrl.cpu().numpy()

@@ -289,3 +289,37 @@ def test_early_exit_after_convergence_is_a_noop(kernels, default_sim, golden):
     assert r1.n_iter == r2.n_iter
     np.testing.assert_array_equal(r1.G, r2.G)
     np.testing.assert_array_equal(r1.C, r2.C)
+
+
+@pytest.mark.parametrize("shape_k", [((1000, 1000), 8), ((600, 1500), 6), ((1500, 400), 12)])
+def test_device_nndsvdar_init_matches_sklearn(kernels, default_sim, shape_k, sweep_path):
+    """Row a4/f1: randomized SVD + NNDSVDar with the 16 passes over X on the device; same RNG stream."""
+    from sklearn.decomposition._nmf import _initialize_nmf
+    from scrna_b200.nmf_init import nndsvdar_init_device
+    from scrna_b200.nmf_solver import DeviceMatrix
+    (g, n), k = shape_k
+    if (g, n) == (1000, 1000):
+        X = default_sim["src"]
+    else:
+        rng = np.random.RandomState(g + n)
+        mu = rng.gamma(2.0, 1.0, size=(g, 1)) * (1 + (rng.rand(g, 6) < 0.2) @ (rng.rand(6, n) < 0.3) * 3.0)
+        X = rng.poisson(mu).astype(np.float64)
+    W0, H0, XT = nndsvdar_init_device(DeviceMatrix.from_host(X, kernels), k, kernels, seed=0)
+    Wr, Hr = _initialize_nmf(X, k, init="nndsvdar", random_state=0)
+    assert XT is not None and W0.shape == Wr.shape and H0.shape == Hr.shape
+    # the zero pattern decides where the random fill lands: it must agree for the fills to line up
+    big_w, big_h = Wr > 1e-3 * Wr.max(), Hr > 1e-3 * Hr.max()
+    assert rel_fro(W0[big_w], Wr[big_w]) < 1e-4 and rel_fro(H0[big_h], Hr[big_h]) < 1e-4
+    assert rel_fro(W0, Wr) < 1e-3 and rel_fro(H0, Hr) < 1e-3
+
+
+def test_nmf_clustering_with_device_init(kernels, default_sim, golden):
+    """NmfClustering.apply(init='device') lands on the reference's factorization (same labels, n_iter +-1)."""
+    from scrna_b200 import NmfClustering
+    g = golden("nmf_source")
+    nmf = NmfClustering(default_sim["src"], default_sim["gene_ids"], 8, default_sim["src_labels"])
+    nmf.apply(k=8, init='device', **CLI)
+    assert abs(nmf.n_iter - int(g["nmf_n_iter"])) <= 1
+    assert rel_fro(nmf.dictionary, g["nmf_W"]) < TOL_FACTOR
+    assert rel_fro(nmf.data_matrix, g["nmf_H"]) < TOL_FACTOR
+    np.testing.assert_array_equal(nmf.cluster_labels, g["nmf_labels"])
