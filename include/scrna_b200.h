@@ -244,6 +244,22 @@ int scrna_row_sqnorm_f64(const double* AT, int64_t ld, int n, double* out, void*
 int scrna_gather_vectors_f64(const double* VT, int64_t ld, int n, const int32_t* order, int c, double* out,
                              int64_t ldo, void* stream);
 
+/* K13 at scale: block one-sided Jacobi on N = M^T (sc3_svd_block.cu).  W (n_pad x ld, n_pad = 32 *
+ * scrna_bjacobi_blocks(n), rows >= n zero) starts as a copy of M; one call = one sweep (all block pairs once:
+ * pair Gram -> 64 x 64 eigenproblem in shared memory -> rotation of the 64 rows, two GEMM-shaped kernels);
+ * `rotated` += block pairs that still had a coupling above 1e-11 (0 after a sweep == converged).  Afterwards
+ * row j of W is sigma_j * v_j: scrna_row_sqnorm_f64 gives sigma^2, scrna_gather_scaled_f64 the unit vectors.
+ * Columns whose squared norm is <= null_sq (numerically null: pass (1e-12 sigma_max)^2) are never rotated.
+ * work: scrna_bjacobi_work_elems(n) doubles.  n > 32. */
+int scrna_bjacobi_blocks(int n);
+int scrna_bjacobi_splits(int n);
+int64_t scrna_bjacobi_work_elems(int n);
+int scrna_bjacobi_sweep_f64(double* W, int64_t ld, int n, double tol, double null_sq, double* work,
+                            int32_t* rotated, void* stream);
+/* out[i][r] = W[order[r]][i] * scale[order[r]], r < c. */
+int scrna_gather_scaled_f64(const double* W, int64_t ld, int n, const int32_t* order, const double* scale, int c,
+                            double* out, int64_t ldo, void* stream);
+
 /* K14-K17 k-means as sklearn KMeans(init='k-means++', algorithm='lloyd') runs it
  * (sc3_clustering_impl.py:215-217).  state: 8 doubles {tol, potential, shift_tot, inertia, changed, n_empty}. */
 int scrna_km_prepare(const double* V, int64_t ldv, int n, int d, double* X, int64_t ldx, double* xsq,

@@ -71,6 +71,11 @@ _SIGNATURES = {
     "scrna_jacobi_sweep_f64": [c_ptr, c_ptr, c_i64, c_int, c_dbl, c_ptr, c_ptr],
     "scrna_row_sqnorm_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr],
     "scrna_gather_vectors_f64": [c_ptr, c_i64, c_int, c_ptr, c_int, c_ptr, c_i64, c_ptr],
+    "scrna_bjacobi_blocks": [c_int],
+    "scrna_bjacobi_splits": [c_int],
+    "scrna_bjacobi_work_elems": [c_int],
+    "scrna_bjacobi_sweep_f64": [c_ptr, c_i64, c_int, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr],
+    "scrna_gather_scaled_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr],
     "scrna_km_prepare": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_kmeans_pp": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_dbl, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                         c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
@@ -88,10 +93,11 @@ _SIGNATURES = {
 # entry points that return a count / version instead of a status code
 _VALUE_RETURNING = {"scrna_abi_version", "scrna_nmf_xht_splits", "scrna_nmf_wtx_splits", "scrna_nmf_gram_blocks",
                     "scrna_nmf_update_blocks", "scrna_residual_blocks", "scrna_nmf_tc_supported", "scrna_nmf_wtx_tc_splits",
-                    "scrna_nmf_tc_shadow_elems"}
+                    "scrna_nmf_tc_shadow_elems", "scrna_bjacobi_blocks", "scrna_bjacobi_splits",
+                    "scrna_bjacobi_work_elems"}
 
 
-_RETURNS_I64 = {"scrna_nmf_tc_shadow_elems"}
+_RETURNS_I64 = {"scrna_nmf_tc_shadow_elems", "scrna_bjacobi_work_elems"}
 
 
 class ScrnaError(RuntimeError):

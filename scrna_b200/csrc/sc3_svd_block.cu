@@ -1,0 +1,296 @@
+// K13 at scale: right singular vectors of the n x n SC3 matrix by BLOCK one-sided Jacobi in fp64.
+//
+// The reference takes a full LAPACK SVD (scipy.linalg.svd, sc3_clustering_impl.py:178) and keeps the first
+// `components` right singular vectors (sc3_clustering.py:95-98).  The spectrum below the few cluster
+// directions is a flat noise bulk (neighbouring singular values 0.1 % apart at rank 0.07 n), which no
+// subspace / Krylov iteration resolves; a dense O(n^3) method is needed, and it has to be GEMM-shaped to run
+// at the FP64 pipe's rate instead of HBM's (the unblocked kernel in sc3_transform.cu streams the whole
+// matrix once per rotation round: 32 n^3 bytes per sweep).
+//
+// Formulation.  One-sided Jacobi is applied to N = M^T: rotations R orthogonalise the columns of N, and at
+// convergence N.R = V.Sigma where V are the LEFT singular vectors of N = the RIGHT singular vectors of M.
+// Column j of N is row j of M, so the working array W (row j = column j of N.R) starts as M itself, no
+// transposition and no accumulated rotation matrix: v_j = W[j] / |W[j]|, sigma_j = |W[j]|.
+//
+// Blocking.  Columns are grouped in blocks of 32; a round pairs the blocks (round-robin tournament) and for
+// every pair (I, J), independently:
+//   1. gram   : G = [W_I; W_J] . [W_I; W_J]^T                 (64 x 64, reduction over n, split partials)
+//   2. eigen  : two-sided cyclic Jacobi on G in shared memory  -> U (64 x 64 orthogonal), G.U = U.diag
+//   3. apply  : [W_I; W_J] <- U^T . [W_I; W_J]                  (64 x 64 times 64 x n)
+// A sweep is nblk-1 rounds; traffic per sweep drops from 32 n^3 to n^3 bytes and the work is two GEMMs.
+#include "common.cuh"
+
+namespace scrna {
+
+constexpr int BJ_B = 32;          // columns per block
+constexpr int BJ_P = 2 * BJ_B;    // columns per pair
+constexpr int BJ_LD = BJ_P + 1;   // shared-memory pitch (doubles)
+
+__device__ __forceinline__ void bj_pair(int m, int round, int i, int& p, int& q) {
+  const int mm = m - 1;
+  if (i == 0) { p = round % mm; q = mm; }
+  else { p = (round + i) % mm; q = (round - i + mm) % mm; }
+  if (p > q) { const int t = p; p = q; q = t; }
+}
+
+// ---- 1. pair Gram partials: part[pair][split][64*64] ------------------------------------------------
+// The 64 x 32 chunk is staged TRANSPOSED ([k][row], pitch 66) so that a thread's four rows / four columns are
+// two 128-bit shared-memory loads each.  (An 8 x 8 register-tile variant measured slower: 2.8 vs 4.3 TFMA/s,
+// its 186 registers leave one CTA per SM and nothing to overlap the staging with.)
+constexpr int BJ_TP = BJ_P + 2;
+constexpr int BJ_KC = 32;         // reduction chunk of the Gram kernel
+__global__ void __launch_bounds__(256)
+bj_gram_kernel(const double* __restrict__ W, int64_t ld, int n, int nblk, int m, int round, int nsplit,
+               double* __restrict__ part) {
+  int p, q;
+  bj_pair(m, round, blockIdx.x, p, q);
+  if (q >= nblk) return;  // bye
+  __shared__ __align__(16) double tile[BJ_KC][BJ_TP];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int per = (int)(((int64_t)n + nsplit - 1) / nsplit);
+  const int c_begin = blockIdx.y * per;
+  const int c_end = min(n, c_begin + per);
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int c0 = c_begin; c0 < c_end; c0 += BJ_KC) {
+    __syncthreads();
+    for (int e = tid; e < BJ_P * BJ_KC; e += 256) {
+      const int r = e / BJ_KC, c = e % BJ_KC;
+      const int64_t row = (r < BJ_B) ? (int64_t)p * BJ_B + r : (int64_t)q * BJ_B + (r - BJ_B);
+      tile[c][r] = (c0 + c < c_end) ? W[row * ld + c0 + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < BJ_KC; ++kk) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&tile[kk][4 * ty]);
+      const double2 a23 = *reinterpret_cast<const double2*>(&tile[kk][4 * ty + 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&tile[kk][4 * tx]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&tile[kk][4 * tx + 2]);
+      const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+      const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+  }
+  double* out = part + ((int64_t)blockIdx.x * nsplit + blockIdx.y) * (BJ_P * BJ_P);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[(4 * ty + i) * BJ_P + 4 * tx + j] = acc[i][j];
+}
+
+// ---- 2. eigenvectors of the 64 x 64 pair Gram: U[pair][64*64] (row-major, G.U = U.diag) ---------------
+__global__ void __launch_bounds__(256)
+bj_eigen_kernel(const double* __restrict__ part, int nsplit, int nblk, int m, int round, double tol,
+                double null_sq, double* __restrict__ Uout, int* __restrict__ rotated) {
+  int p, q;
+  bj_pair(m, round, blockIdx.x, p, q);
+  if (q >= nblk) return;
+  extern __shared__ double bj_smem[];
+  double* G = bj_smem;                  // 64 x 65
+  double* U = G + BJ_P * BJ_LD;         // 64 x 65
+  __shared__ double cs[BJ_B][2];
+  __shared__ int pq[BJ_B][2];
+  __shared__ int any_rot, big_rot;
+  const int tid = threadIdx.x;
+  const double* src = part + (int64_t)blockIdx.x * nsplit * (BJ_P * BJ_P);
+  for (int e = tid; e < BJ_P * BJ_P; e += 256) {
+    double s = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) s += src[(int64_t)sp * (BJ_P * BJ_P) + e];  // fixed order
+    const int r = e / BJ_P, c = e % BJ_P;
+    G[r * BJ_LD + c] = s;
+    U[r * BJ_LD + c] = (r == c) ? 1.0 : 0.0;
+  }
+  if (tid == 0) big_rot = 0;
+  __syncthreads();
+  // symmetrise (the two triangles were summed in different orders)
+  for (int e = tid; e < BJ_P * BJ_P; e += 256) {
+    const int r = e / BJ_P, c = e % BJ_P;
+    if (r < c) {
+      const double v = 0.5 * (G[r * BJ_LD + c] + G[c * BJ_LD + r]);
+      G[r * BJ_LD + c] = v;
+      G[c * BJ_LD + r] = v;
+    }
+  }
+  __syncthreads();
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    if (tid == 0) any_rot = 0;
+    __syncthreads();
+    for (int step = 0; step < BJ_P - 1; ++step) {
+      if (tid < BJ_B) {
+        int a, b;
+        bj_pair(BJ_P, step, tid, a, b);
+        const double gaa = G[a * BJ_LD + a], gbb = G[b * BJ_LD + b], gab = G[a * BJ_LD + b];
+        double c = 1.0, s = 0.0;
+        // columns below the numerical-null threshold are left alone: they are noise and would rotate forever
+        if (gaa > null_sq && gbb > null_sq && fabs(gab) > tol * sqrt(gaa * gbb)) {
+          const double zeta = (gbb - gaa) / (2.0 * gab);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(1.0 + t * t);
+          s = c * t;
+          any_rot = 1;
+          // only couplings above the Gram's own rounding floor keep the outer sweep loop alive
+          if (fabs(gab) > 1e-11 * sqrt(gaa * gbb)) big_rot = 1;
+        }
+        cs[tid][0] = c; cs[tid][1] = s;
+        pq[tid][0] = a; pq[tid][1] = b;
+      }
+      __syncthreads();
+      // rows: G <- J^T G   (row a' = c.a - s.b ; row b' = s.a + c.b)
+      for (int e = tid; e < BJ_B * BJ_P; e += 256) {
+        const int pr = e / BJ_P, col = e % BJ_P;
+        const double c = cs[pr][0], s = cs[pr][1];
+        if (s != 0.0) {
+          const int a = pq[pr][0], b = pq[pr][1];
+          const double x = G[a * BJ_LD + col], y = G[b * BJ_LD + col];
+          G[a * BJ_LD + col] = c * x - s * y;
+          G[b * BJ_LD + col] = s * x + c * y;
+        }
+      }
+      __syncthreads();
+      // columns: G <- G J, U <- U J
+      for (int e = tid; e < BJ_B * BJ_P; e += 256) {
+        const int pr = e / BJ_P, row = e % BJ_P;
+        const double c = cs[pr][0], s = cs[pr][1];
+        if (s != 0.0) {
+          const int a = pq[pr][0], b = pq[pr][1];
+          double x = G[row * BJ_LD + a], y = G[row * BJ_LD + b];
+          G[row * BJ_LD + a] = c * x - s * y;
+          G[row * BJ_LD + b] = s * x + c * y;
+          x = U[row * BJ_LD + a]; y = U[row * BJ_LD + b];
+          U[row * BJ_LD + a] = c * x - s * y;
+          U[row * BJ_LD + b] = s * x + c * y;
+        }
+      }
+      __syncthreads();
+    }
+    if (!any_rot) break;
+    __syncthreads();
+  }
+  double* dst = Uout + (int64_t)blockIdx.x * (BJ_P * BJ_P);
+  for (int e = tid; e < BJ_P * BJ_P; e += 256) dst[e] = U[(e / BJ_P) * BJ_LD + (e % BJ_P)];
+  if (tid == 0 && big_rot) atomicAdd(rotated, 1);
+}
+
+// ---- 3. apply: rows [I; J] of W  <-  U^T . rows -----------------------------------------------------
+__global__ void __launch_bounds__(256)
+bj_apply_kernel(double* __restrict__ W, int64_t ld, int n, int nblk, int m, int round,
+                const double* __restrict__ Uall) {
+  int p, q;
+  bj_pair(m, round, blockIdx.x, p, q);
+  if (q >= nblk) return;
+  extern __shared__ __align__(16) double bj_smem[];
+  double* Us = bj_smem;                 // [s][r]   64 x 66
+  double* T = Us + BJ_P * BJ_TP;        // [s][col] 64 x 66
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int c0 = blockIdx.y * BJ_P;
+  const double* Ug = Uall + (int64_t)blockIdx.x * (BJ_P * BJ_P);
+  for (int e = tid; e < BJ_P * BJ_P; e += 256) {
+    const int s = e / BJ_P, c = e % BJ_P;
+    Us[s * BJ_TP + c] = Ug[e];
+    const int64_t row = (s < BJ_B) ? (int64_t)p * BJ_B + s : (int64_t)q * BJ_B + (s - BJ_B);
+    T[s * BJ_TP + c] = (c0 + c < n) ? W[row * ld + c0 + c] : 0.0;
+  }
+  __syncthreads();
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 8
+  for (int s = 0; s < BJ_P; ++s) {
+    const double2 a01 = *reinterpret_cast<const double2*>(&Us[s * BJ_TP + 4 * ty]);
+    const double2 a23 = *reinterpret_cast<const double2*>(&Us[s * BJ_TP + 4 * ty + 2]);
+    const double2 b01 = *reinterpret_cast<const double2*>(&T[s * BJ_TP + 4 * tx]);
+    const double2 b23 = *reinterpret_cast<const double2*>(&T[s * BJ_TP + 4 * tx + 2]);
+    const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+    const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 4 * ty + i;
+    const int64_t row = (r < BJ_B) ? (int64_t)p * BJ_B + r : (int64_t)q * BJ_B + (r - BJ_B);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + 4 * tx + j;
+      if (c < n) W[row * ld + c] = acc[i][j];
+    }
+  }
+}
+
+// out[i][r] = W[order[r]][i] * scale[order[r]]  (the kept right singular vectors as unit columns)
+__global__ void bj_gather_kernel(const double* __restrict__ W, int64_t ld, int n, const int* __restrict__ order,
+                                 const double* __restrict__ scale, int c, double* __restrict__ out, int64_t ldo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (i >= n || r >= c) return;
+  const int src = order[r];
+  out[(int64_t)i * ldo + r] = W[(int64_t)src * ld + i] * scale[src];
+}
+
+}  // namespace scrna
+
+using namespace scrna;
+
+extern "C" int scrna_bjacobi_blocks(int n) { return (int)ceil_div(n, BJ_B); }
+
+extern "C" int scrna_bjacobi_splits(int n) {
+  // enough Gram CTAs (pairs x splits) for two per SM, spans of at least 256 columns
+  const int pairs = (scrna_bjacobi_blocks(n) + 1) / 2;
+  int s = (int)ceil_div(2 * (int64_t)num_sms(), pairs > 0 ? pairs : 1);
+  if (s > n / 256) s = n / 256;
+  if (s < 1) s = 1;
+  if (s > 16) s = 16;
+  return s;
+}
+
+// work: pairs * (splits + 1) * 4096 doubles, pairs = ceil(nblk / 2)
+extern "C" int64_t scrna_bjacobi_work_elems(int n) {
+  const int nblk = scrna_bjacobi_blocks(n);
+  const int m = (nblk + 1) / 2 * 2;
+  return (int64_t)(m / 2) * (scrna_bjacobi_splits(n) + 1) * (BJ_P * BJ_P);
+}
+
+extern "C" int scrna_bjacobi_sweep_f64(double* W, int64_t ld, int n, double tol, double null_sq, double* work,
+                                       int32_t* rotated, void* stream) {
+  if (!W || !work || !rotated || n <= 0 || ld < n) return SCRNA_ERR_BADARG;
+  const int nblk = scrna_bjacobi_blocks(n);
+  if (nblk < 2) return SCRNA_ERR_UNSUPPORTED;  // n <= 32: use the unblocked kernel (scrna_jacobi_sweep_f64)
+  const int m = (nblk + 1) / 2 * 2;
+  const int pairs = m / 2;
+  const int nsplit = scrna_bjacobi_splits(n);
+  double* part = work;
+  double* U = work + (int64_t)pairs * nsplit * (BJ_P * BJ_P);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static bool attr = false;
+  const size_t smem = 2 * (size_t)BJ_P * BJ_LD * sizeof(double);
+  const size_t smem_apply = 2 * (size_t)BJ_P * BJ_TP * sizeof(double);
+  if (!attr) {
+    cudaFuncSetAttribute(bj_eigen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_apply);
+    attr = true;
+  }
+  for (int round = 0; round < m - 1; ++round) {
+    bj_gram_kernel<<<dim3(pairs, nsplit), 256, 0, st>>>(W, ld, n, nblk, m, round, nsplit, part);
+    bj_eigen_kernel<<<pairs, 256, smem, st>>>(part, nsplit, nblk, m, round, tol, null_sq, U, rotated);
+    bj_apply_kernel<<<dim3(pairs, (unsigned)ceil_div(n, BJ_P)), 256, smem_apply, st>>>(W, ld, n, nblk, m, round, U);
+  }
+  return last_launch_status();
+}
+
+extern "C" int scrna_gather_scaled_f64(const double* W, int64_t ld, int n, const int32_t* order, const double* scale,
+                                       int c, double* out, int64_t ldo, void* stream) {
+  if (!W || !order || !scale || !out || n <= 0 || c <= 0 || ldo < c) return SCRNA_ERR_BADARG;
+  bj_gather_kernel<<<dim3((unsigned)ceil_div(n, 256), c), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      W, ld, n, order, scale, c, out, ldo);
+  return last_launch_status();
+}

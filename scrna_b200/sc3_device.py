@@ -102,11 +102,17 @@ class Sc3Ops:
                 print("All values are Zero!")
         return out
 
-    def right_singular_vectors(self, M, components, max_sweeps=40, tol=1e-15):
+    def right_singular_vectors(self, M, components, max_sweeps=40, tol=1e-15, blocked=None):
         """First `components` right singular vectors of the n x n device matrix M (descending singular
-        values) by one-sided Jacobi; returns (V device n x components, singular values numpy n)."""
+        values) by one-sided Jacobi; returns (V device n x components, singular values numpy n).
+        n > 64 runs the block algorithm (sc3_svd_block.cu: GEMM-shaped, FP64-pipe bound), smaller matrices
+        the unblocked kernel."""
         t = self.torch
         n = M.shape[0]
+        if blocked is None:
+            blocked = n > 64
+        if blocked:
+            return self._rsv_blocked(M, components, max_sweeps, tol)
         AT = self.empty(n, n)
         VT = self.empty(n, n)
         self._call("scrna_jacobi_init_f64", M, n, n, AT, VT, n, self._s(), launches=2)
@@ -128,6 +134,40 @@ class Sc3Ops:
         od = t.from_numpy(order[:c].copy()).to(self.dev)
         V = self.empty(n, c)
         self._call("scrna_gather_vectors_f64", VT, n, n, od, c, V, c, self._s())
+        return V, vals[order]
+
+    def _rsv_blocked(self, M, components, max_sweeps, tol):
+        t = self.torch
+        n = M.shape[0]
+        n_pad = 32 * _lib.call("scrna_bjacobi_blocks", n)
+        W = self.zeros(n_pad, n)
+        W[:n].copy_(M)                       # N = M^T: column j of N is row j of M
+        work = self.empty(_lib.call("scrna_bjacobi_work_elems", n))
+        rotated = self.zeros(1, dtype=t.int32)
+        rounds = (n_pad // 32 + 1) // 2 * 2 - 1
+        self.jacobi_sweeps = 0
+        # numerically-null threshold: |M|_F^2 >= sigma_max^2 bounds it from above, row norms from below
+        sq0 = self.empty(n)
+        self._call("scrna_row_sqnorm_f64", W, n, n, sq0, self._s())
+        null_sq = 1e-24 * float(sq0.max().cpu())
+        for _ in range(max_sweeps):
+            rotated.zero_()
+            self._call("scrna_bjacobi_sweep_f64", W, n, n, float(tol), null_sq, work, rotated, self._s(),
+                       launches=3 * rounds)
+            self.jacobi_sweeps += 1
+            if int(rotated.cpu()[0]) == 0:
+                break
+        sq = self.empty(n)
+        self._call("scrna_row_sqnorm_f64", W, n, n, sq, self._s())
+        vals = np.sqrt(np.maximum(sq.cpu().numpy(), 0.0))
+        order = np.argsort(-vals, kind="stable").astype(np.int32)
+        c = int(components)
+        with np.errstate(divide="ignore"):
+            inv = np.where(vals > 0, 1.0 / vals, 0.0)
+        od = t.from_numpy(order[:c].copy()).to(self.dev)
+        sc = t.from_numpy(inv).to(self.dev)
+        V = self.empty(n, c)
+        self._call("scrna_gather_scaled_f64", W, n, n, od, sc, c, V, c, self._s())
         return V, vals[order]
 
     # ---- a14 k-means ----------------------------------------------------------------------------------
