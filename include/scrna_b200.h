@@ -270,8 +270,9 @@ int scrna_kmeans_pp(const double* X, int64_t ldx, int n, int d, const double* xs
                     void* stream);
 int scrna_lloyd_assign(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc, int k,
                        int32_t* labels, void* stream);
+int64_t scrna_lloyd_sums_work_elems(int k, int d);
 int scrna_lloyd_sums(const double* X, int64_t ldx, int n, int d, const int32_t* labels, int k, double* sums,
-                     int64_t lds, int32_t* counts, void* stream);
+                     int64_t lds, int32_t* counts, double* work, void* stream);
 int scrna_lloyd_finish(double* Cnew, const double* Cold, int64_t ldc, int k, int d, const int32_t* counts,
                        const int32_t* labels, int32_t* labels_old, int n, double* state, void* stream);
 int scrna_km_cell_dist(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc,

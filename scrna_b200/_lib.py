@@ -80,7 +80,8 @@ _SIGNATURES = {
     "scrna_kmeans_pp": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_dbl, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                         c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     "scrna_lloyd_assign": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_int, c_ptr, c_ptr],
-    "scrna_lloyd_sums": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_ptr, c_i64, c_ptr, c_ptr],
+    "scrna_lloyd_sums": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr],
+    "scrna_lloyd_sums_work_elems": [c_int, c_int],
     "scrna_lloyd_finish": [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr],
     "scrna_km_cell_dist": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr],
     "scrna_km_inertia": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
@@ -94,10 +95,10 @@ _SIGNATURES = {
 _VALUE_RETURNING = {"scrna_abi_version", "scrna_nmf_xht_splits", "scrna_nmf_wtx_splits", "scrna_nmf_gram_blocks",
                     "scrna_nmf_update_blocks", "scrna_residual_blocks", "scrna_nmf_tc_supported", "scrna_nmf_wtx_tc_splits",
                     "scrna_nmf_tc_shadow_elems", "scrna_bjacobi_blocks", "scrna_bjacobi_splits",
-                    "scrna_bjacobi_work_elems"}
+                    "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems"}
 
 
-_RETURNS_I64 = {"scrna_nmf_tc_shadow_elems", "scrna_bjacobi_work_elems"}
+_RETURNS_I64 = {"scrna_nmf_tc_shadow_elems", "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems"}
 
 
 class ScrnaError(RuntimeError):

@@ -208,22 +208,56 @@ lloyd_assign_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, con
   if (lane == 0) labels[i] = bj;
 }
 
-// sums[j][f] = sum over cells with label j, in cell order; counts[j]
+// sums[j][f] = sum over cells with label j; counts[j].  The cells are cut into KM_SEG fixed segments: a
+// block owns 128 features of one segment and adds each cell (in cell order) into the shared-memory row of its
+// label -- one pass over X for all k clusters; the segment partials are then added in segment order, so the
+// result is deterministic (sklearn's own order depends on its OpenMP chunking, _k_means_lloyd.pyx:168-218).
+constexpr int KM_SEG = 32;
 __global__ void __launch_bounds__(128)
-lloyd_sums_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const int* __restrict__ labels,
-                  double* __restrict__ sums, int64_t lds, int* __restrict__ counts) {
+lloyd_sums_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const int* __restrict__ labels, int k,
+                  double* __restrict__ psum, int* __restrict__ pcnt) {
+  extern __shared__ double sacc[];  // k x 128
+  const int seg = blockIdx.y, tid = threadIdx.x;
+  const int f = blockIdx.x * 128 + tid;
+  const int per = (n + KM_SEG - 1) / KM_SEG;
+  const int i0 = seg * per, i1 = min(n, i0 + per);
+  for (int j = 0; j < k; ++j) sacc[j * 128 + tid] = 0.0;
+  if (f < d) {
+    const double* xf = X + f;
+    int i = i0;
+    for (; i + 4 <= i1; i += 4) {  // four independent loads in flight, accumulation still in cell order
+      const int l0 = labels[i], l1 = labels[i + 1], l2 = labels[i + 2], l3 = labels[i + 3];
+      const double x0 = xf[(int64_t)i * ldx], x1 = xf[(int64_t)(i + 1) * ldx], x2 = xf[(int64_t)(i + 2) * ldx],
+                   x3 = xf[(int64_t)(i + 3) * ldx];
+      sacc[l0 * 128 + tid] += x0;
+      sacc[l1 * 128 + tid] += x1;
+      sacc[l2 * 128 + tid] += x2;
+      sacc[l3 * 128 + tid] += x3;
+    }
+    for (; i < i1; ++i) sacc[labels[i] * 128 + tid] += xf[(int64_t)i * ldx];
+    for (int j = 0; j < k; ++j) psum[((int64_t)seg * k + j) * d + f] = sacc[j * 128 + tid];
+  }
+  if (blockIdx.x == 0 && tid < k) {
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) cnt += (labels[i] == tid);
+    pcnt[seg * k + tid] = cnt;
+  }
+}
+
+__global__ void lloyd_sums_final_kernel(const double* __restrict__ psum, const int* __restrict__ pcnt, int k, int d,
+                                        double* __restrict__ sums, int64_t lds, int* __restrict__ counts) {
   const int j = blockIdx.y;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  double s = 0.0;
-  int cnt = 0;
-  for (int i = 0; i < n; ++i) {
-    if (labels[i] == j) {
-      ++cnt;
-      if (f < d) s += X[(int64_t)i * ldx + f];
-    }
+  if (f < d) {
+    double s = 0.0;
+    for (int seg = 0; seg < KM_SEG; ++seg) s += psum[((int64_t)seg * k + j) * d + f];
+    sums[(int64_t)j * lds + f] = s;
   }
-  if (f < d) sums[(int64_t)j * lds + f] = s;
-  if (blockIdx.x == 0 && threadIdx.x == 0) counts[j] = cnt;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int c = 0;
+    for (int seg = 0; seg < KM_SEG; ++seg) c += pcnt[seg * k + j];
+    counts[j] = c;
+  }
 }
 
 // averages, empty-cluster handling (copy from the heaviest cluster, _k_means_common.pyx:262-280), shifts,
@@ -410,11 +444,24 @@ extern "C" int scrna_lloyd_assign(const double* X, int64_t ldx, int n, int d, co
   return last_launch_status();
 }
 
+extern "C" int64_t scrna_lloyd_sums_work_elems(int k, int d) { return (int64_t)KM_SEG * k * (d + 1); }
+
 extern "C" int scrna_lloyd_sums(const double* X, int64_t ldx, int n, int d, const int32_t* labels, int k,
-                                double* sums, int64_t lds, int32_t* counts, void* stream) {
-  if (!X || !labels || !sums || !counts || n <= 0 || d <= 0 || k <= 0 || ldx < d || lds < d) return SCRNA_ERR_BADARG;
-  dim3 grid((unsigned)ceil_div(d, 128), (unsigned)k);
-  lloyd_sums_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(X, ldx, n, d, labels, sums, lds, counts);
+                                double* sums, int64_t lds, int32_t* counts, double* work, void* stream) {
+  if (!X || !labels || !sums || !counts || !work || n <= 0 || d <= 0 || k <= 0 || k > 128 || ldx < d || lds < d)
+    return SCRNA_ERR_BADARG;
+  double* psum = work;                                                     // KM_SEG x k x d
+  int* pcnt = reinterpret_cast<int*>(work + (int64_t)KM_SEG * k * d);      // KM_SEG x k ints
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)k * 128 * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(lloyd_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
+    attr = true;
+  }
+  lloyd_sums_kernel<<<dim3((unsigned)ceil_div(d, 128), KM_SEG), 128, smem, st>>>(X, ldx, n, d, labels, k, psum, pcnt);
+  lloyd_sums_final_kernel<<<dim3((unsigned)ceil_div(d, 128), (unsigned)k), 128, 0, st>>>(psum, pcnt, k, d, sums, lds,
+                                                                                       counts);
   return last_launch_status();
 }
 

@@ -65,10 +65,12 @@ bj_gram_kernel(const double* __restrict__ W, int64_t ld, int n, int nblk, int m,
     __syncthreads();
 #pragma unroll 8
     for (int kk = 0; kk < BJ_KC; ++kk) {
-      const double2 a01 = *reinterpret_cast<const double2*>(&tile[kk][4 * ty]);
-      const double2 a23 = *reinterpret_cast<const double2*>(&tile[kk][4 * ty + 2]);
-      const double2 b01 = *reinterpret_cast<const double2*>(&tile[kk][4 * tx]);
-      const double2 b23 = *reinterpret_cast<const double2*>(&tile[kk][4 * tx + 2]);
+      // thread (ty, tx) owns rows {2ty, 2ty+1, 32+2ty, 33+2ty} x columns {2tx, 2tx+1, 32+2tx, 33+2tx}: the 16
+      // lanes of a half-warp read 256 contiguous bytes per load (no half-used shared-memory wavefronts)
+      const double2 a01 = *reinterpret_cast<const double2*>(&tile[kk][2 * ty]);
+      const double2 a23 = *reinterpret_cast<const double2*>(&tile[kk][32 + 2 * ty]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&tile[kk][2 * tx]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&tile[kk][32 + 2 * tx]);
       const double a[4] = {a01.x, a01.y, a23.x, a23.y};
       const double b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
@@ -81,11 +83,13 @@ bj_gram_kernel(const double* __restrict__ W, int64_t ld, int n, int nblk, int m,
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[(4 * ty + i) * BJ_P + 4 * tx + j] = acc[i][j];
+    for (int j = 0; j < 4; ++j)
+      out[((i < 2 ? 0 : 32 - 2) + 2 * ty + i) * BJ_P + (j < 2 ? 0 : 32 - 2) + 2 * tx + j] = acc[i][j];
 }
 
 // ---- 2. eigenvectors of the 64 x 64 pair Gram: U[pair][64*64] (row-major, G.U = U.diag) ---------------
-__global__ void __launch_bounds__(256)
+constexpr int BJ_ET = 1024;  // threads of the eigen kernel: one CTA per pair, at most one pair per SM
+__global__ void __launch_bounds__(BJ_ET)
 bj_eigen_kernel(const double* __restrict__ part, int nsplit, int nblk, int m, int round, double tol,
                 double null_sq, double* __restrict__ Uout, int* __restrict__ rotated) {
   int p, q;
@@ -99,7 +103,7 @@ bj_eigen_kernel(const double* __restrict__ part, int nsplit, int nblk, int m, in
   __shared__ int any_rot, big_rot;
   const int tid = threadIdx.x;
   const double* src = part + (int64_t)blockIdx.x * nsplit * (BJ_P * BJ_P);
-  for (int e = tid; e < BJ_P * BJ_P; e += 256) {
+  for (int e = tid; e < BJ_P * BJ_P; e += BJ_ET) {
     double s = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) s += src[(int64_t)sp * (BJ_P * BJ_P) + e];  // fixed order
     const int r = e / BJ_P, c = e % BJ_P;
@@ -109,7 +113,7 @@ bj_eigen_kernel(const double* __restrict__ part, int nsplit, int nblk, int m, in
   if (tid == 0) big_rot = 0;
   __syncthreads();
   // symmetrise (the two triangles were summed in different orders)
-  for (int e = tid; e < BJ_P * BJ_P; e += 256) {
+  for (int e = tid; e < BJ_P * BJ_P; e += BJ_ET) {
     const int r = e / BJ_P, c = e % BJ_P;
     if (r < c) {
       const double v = 0.5 * (G[r * BJ_LD + c] + G[c * BJ_LD + r]);
@@ -142,7 +146,7 @@ bj_eigen_kernel(const double* __restrict__ part, int nsplit, int nblk, int m, in
       }
       __syncthreads();
       // rows: G <- J^T G   (row a' = c.a - s.b ; row b' = s.a + c.b)
-      for (int e = tid; e < BJ_B * BJ_P; e += 256) {
+      for (int e = tid; e < BJ_B * BJ_P; e += BJ_ET) {
         const int pr = e / BJ_P, col = e % BJ_P;
         const double c = cs[pr][0], s = cs[pr][1];
         if (s != 0.0) {
@@ -154,7 +158,7 @@ bj_eigen_kernel(const double* __restrict__ part, int nsplit, int nblk, int m, in
       }
       __syncthreads();
       // columns: G <- G J, U <- U J
-      for (int e = tid; e < BJ_B * BJ_P; e += 256) {
+      for (int e = tid; e < BJ_B * BJ_P; e += BJ_ET) {
         const int pr = e / BJ_P, row = e % BJ_P;
         const double c = cs[pr][0], s = cs[pr][1];
         if (s != 0.0) {
@@ -173,7 +177,7 @@ bj_eigen_kernel(const double* __restrict__ part, int nsplit, int nblk, int m, in
     __syncthreads();
   }
   double* dst = Uout + (int64_t)blockIdx.x * (BJ_P * BJ_P);
-  for (int e = tid; e < BJ_P * BJ_P; e += 256) dst[e] = U[(e / BJ_P) * BJ_LD + (e % BJ_P)];
+  for (int e = tid; e < BJ_P * BJ_P; e += BJ_ET) dst[e] = U[(e / BJ_P) * BJ_LD + (e % BJ_P)];
   if (tid == 0 && big_rot) atomicAdd(rotated, 1);
 }
 
@@ -204,10 +208,10 @@ bj_apply_kernel(double* __restrict__ W, int64_t ld, int n, int nblk, int m, int 
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 #pragma unroll 8
   for (int s = 0; s < BJ_P; ++s) {
-    const double2 a01 = *reinterpret_cast<const double2*>(&Us[s * BJ_TP + 4 * ty]);
-    const double2 a23 = *reinterpret_cast<const double2*>(&Us[s * BJ_TP + 4 * ty + 2]);
-    const double2 b01 = *reinterpret_cast<const double2*>(&T[s * BJ_TP + 4 * tx]);
-    const double2 b23 = *reinterpret_cast<const double2*>(&T[s * BJ_TP + 4 * tx + 2]);
+    const double2 a01 = *reinterpret_cast<const double2*>(&Us[s * BJ_TP + 2 * ty]);
+    const double2 a23 = *reinterpret_cast<const double2*>(&Us[s * BJ_TP + 32 + 2 * ty]);
+    const double2 b01 = *reinterpret_cast<const double2*>(&T[s * BJ_TP + 2 * tx]);
+    const double2 b23 = *reinterpret_cast<const double2*>(&T[s * BJ_TP + 32 + 2 * tx]);
     const double a[4] = {a01.x, a01.y, a23.x, a23.y};
     const double b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
@@ -217,11 +221,11 @@ bj_apply_kernel(double* __restrict__ W, int64_t ld, int n, int nblk, int m, int 
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int r = 4 * ty + i;
+    const int r = (i < 2 ? 0 : 32 - 2) + 2 * ty + i;
     const int64_t row = (r < BJ_B) ? (int64_t)p * BJ_B + r : (int64_t)q * BJ_B + (r - BJ_B);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = c0 + 4 * tx + j;
+      const int c = c0 + (j < 2 ? 0 : 32 - 2) + 2 * tx + j;
       if (c < n) W[row * ld + c] = acc[i][j];
     }
   }
@@ -281,7 +285,7 @@ extern "C" int scrna_bjacobi_sweep_f64(double* W, int64_t ld, int n, double tol,
   }
   for (int round = 0; round < m - 1; ++round) {
     bj_gram_kernel<<<dim3(pairs, nsplit), 256, 0, st>>>(W, ld, n, nblk, m, round, nsplit, part);
-    bj_eigen_kernel<<<pairs, 256, smem, st>>>(part, nsplit, nblk, m, round, tol, null_sq, U, rotated);
+    bj_eigen_kernel<<<pairs, BJ_ET, smem, st>>>(part, nsplit, nblk, m, round, tol, null_sq, U, rotated);
     bj_apply_kernel<<<dim3(pairs, (unsigned)ceil_div(n, BJ_P)), 256, smem_apply, st>>>(W, ld, n, nblk, m, round, U);
   }
   return last_launch_status();

@@ -204,8 +204,10 @@ class Sc3Ops:
         labels_old = self.zeros(n, dtype=i32)
         counts = self.zeros(k, dtype=i32)
         celld = self.empty(n)
+        sums_work = self.empty(_lib.call("scrna_lloyd_sums_work_elems", k, d))
         best = None
         esz = 8
+        self.km_iters = 0
         for r in range(n_init):
             u0 = float(draws[r * per])
             uptr = U.data_ptr() + (r * per + 1) * esz
@@ -216,10 +218,11 @@ class Sc3Ops:
             strict = False
             for _ in range(max_iter):
                 self._call("scrna_lloyd_assign", X, d, n, d, cur, d, k, labels, self._s())
-                self._call("scrna_lloyd_sums", X, d, n, d, labels, k, nxt, d, counts, self._s())
+                self._call("scrna_lloyd_sums", X, d, n, d, labels, k, nxt, d, counts, sums_work, self._s(), launches=2)
                 self._call("scrna_km_relocate", X, d, n, d, cur, d, nxt, d, counts, labels, celld, k, self._s())
                 self._call("scrna_lloyd_finish", nxt, cur, d, k, d, counts, labels, labels_old, n, state, self._s())
                 st = state.cpu().numpy()
+                self.km_iters += 1
                 cur, nxt = nxt, cur
                 if st[4] == 0.0:
                     strict = True

@@ -1,1 +1,2 @@
-timeout 1500 python tools/sc3_bench.py --cells 20000 --genes 20000 --no-cpu --single --out gpurun_out/sc3_bench20k.json > gpurun_out/sc3_bench20k.log 2>&1; echo rc=$? >> gpurun_out/sc3_bench20k.log
+python -m pytest tests/test_gpu_sc3.py tests/test_gpu_pipeline.py -m gpu -x -q 2>&1 | tail -4 > gpurun_out/t_gpu.log
+timeout 300 python tools/svd_bench.py 2000 8000 > gpurun_out/svd_plain.log 2>&1
