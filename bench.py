@@ -165,6 +165,52 @@ def cpu_sample(sample_cells, seed=1234):
     return X
 
 
+def sc3_consensus_seconds(cells, genes, k=8):
+    """Second half of BASELINE.json's metric ("SC3 consensus s"): the reference CLI's default SC3 configuration
+    (euclidean distances, pca transformation, <= 15 sampled dimensions in [0.04 n, 0.07 n], KMeans n_init=10,
+    consensus matrix, complete linkage; sc3_clustering.py:58-109) on a synthetic target of `cells` cells, device
+    seconds per stage.  The 20 000-cell configuration takes minutes and is recorded under profiles/."""
+    import torch
+    from scrna_b200.sc3_device import Sc3Ops, kmeans_draw_count
+    ops = Sc3Ops()
+    rng = np.random.RandomState(cells)
+    centers = rng.gamma(2.0, 2.0, size=(genes, k))
+    lab = rng.randint(0, k, size=cells)
+    X = rng.poisson(centers[:, lab] * 2.0 ** (0.3 * rng.randn(1, cells))).astype(np.float64)
+    Xd = ops.to_device(X)
+    ops.distances(X[:, :64], "euclidean")  # warm-up
+    stages = {}
+
+    def timed(name, fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        stages[name] = time.perf_counter() - t0
+        return out
+
+    D = timed("distances_euclidean", lambda: ops.distances(Xd, "euclidean"))
+    pc = [max(1, int(np.floor(0.04 * cells))), int(np.ceil(0.07 * cells))]
+    V, _ = timed("pca_right_singular_vectors", lambda: ops.right_singular_vectors(ops.transform_matrix(D, "pca"), pc[1]))
+    dims = list(range(pc[0], pc[1] + 1))
+    if len(dims) > 15:
+        dims = list(np.random.RandomState(0).permutation(dims)[:15])
+    per, _ = kmeans_draw_count(k)
+    draws = [np.random.RandomState(int(d)).random_sample(10 * per) for d in dims]
+    labs = timed("kmeans_ensemble", lambda: [ops.kmeans(V, int(d), k, u) for d, u in zip(dims, draws)])
+
+    def cons():
+        M = ops.coassoc_new(cells)
+        for l in labs:
+            ops.coassoc_add(M, l)
+        return ops.consensus_clustering(ops.consensus_from_counts(M, float(len(labs))), k)
+    timed("consensus_and_linkage", cons)
+    return {"cells": cells, "genes": genes, "k": k, "seconds": sum(stages.values()), "stages": stages,
+            "jacobi_sweeps": ops.jacobi_sweeps, "dims": len(dims),
+            "config": "1 distance (euclidean) x 1 transformation (pca), n_init=10: cmd_target.py defaults",
+            "at_20000_cells": "profiles/r01_sc3_20k_cells_stage_seconds.json"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -343,6 +389,10 @@ def run_gpu(args):
                                   "numpy/BLAS on all host threads) on %d genes x %d cells; scaled linearly in cells to %d"
                                   % (CPU_SAMPLE_ITERS, genes, CPU_SAMPLE_CELLS, cells)}
 
+    sc3 = None
+    if rank == 0 and world == 1 and args.sc3_cells > 0:
+        torch.cuda.empty_cache()
+        sc3 = sc3_consensus_seconds(args.sc3_cells, args.sc3_cells)
     if rank == 0:
         line = {
             "metric": METRIC if k == K else METRIC.replace("k=8", "k=%d" % k), "value": value, "unit": UNIT,
@@ -358,7 +408,7 @@ def run_gpu(args):
                        "parallelism": "cells sharded x%d, one all-reduce of %d fp64 per iteration"
                                       % (world, k * genes + k * k + 4) if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "sc3_consensus": sc3,
         }
         emit(line)
     if world > 1:
@@ -394,6 +444,8 @@ def main():
     ap.add_argument("--cells", type=int, default=CELLS)
     ap.add_argument("--k", type=int, default=K)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sc3-cells", type=int, default=4000,
+                    help="cells (= genes) of the SC3 consensus timing appended at N=1; 0 skips it")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: stop after the device-timed region")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per sweep launch from the committed ncu capture (profiles/)")

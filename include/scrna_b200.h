@@ -219,6 +219,10 @@ int scrna_reject_stats(const float* X, int64_t ldx, int g, int64_t ncols, const 
  *       (sc3_clustering_impl.py:129-130; also pdist(consensus) at :252 since the consensus is symmetric);
  * op 1: dot product Gram sum_f X[f][i]*X[f][j] (np.corrcoef at :124, spearmanr at :126). */
 int scrna_pairwise_f64(const double* X, int64_t ld, int F, int N, int op, double* out, int64_t ldo, void* stream);
+/* The row block [row_begin, row_end) x N of the same matrix, out[(i - row_begin)][j]: SC3 distances sharded by
+ * row blocks over the GPUs (each rank its rows, then an all-gather); bit-identical to those rows of the full call. */
+int scrna_pairwise_rows_f64(const double* X, int64_t ld, int F, int N, int op, int row_begin, int row_end,
+                            double* out, int64_t ldo, void* stream);
 /* X[:, j] -= mean_f X[f][j] in place; mean (N doubles) is returned (np.cov centring). */
 int scrna_col_center_f64(double* X, int64_t ld, int F, int N, double* mean, void* stream);
 /* out = 1 - corrcoef from the Gram G of centred columns, numpy op order: G/(F-1), /std_i, /std_j, clip. */

@@ -61,6 +61,7 @@ _SIGNATURES = {
                            c_ptr],
     # ---- SC3 ----
     "scrna_pairwise_f64": [c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_i64, c_ptr],
+    "scrna_pairwise_rows_f64": [c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_ptr, c_i64, c_ptr],
     "scrna_col_center_f64": [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr],
     "scrna_corr_epilogue_f64": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr],
     "scrna_rank_avg_f64": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr],

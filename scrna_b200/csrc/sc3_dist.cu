@@ -19,16 +19,22 @@ namespace scrna {
 constexpr int PW_TILE = 64;   // output tile edge
 constexpr int PW_FK = 16;     // features per smem stage
 
+// row_begin < 0: the full symmetric N x N matrix (upper tiles computed, mirrored on write);
+// row_begin >= 0: the row block [row_begin, row_end) x N of it, written to out[(i - row_begin)][j] (SC3
+// distances sharded by row blocks over the GPUs) -- every element by the same instruction
+// sequence as in the symmetric launch, so the block is bit-identical to the corresponding rows.
 template <int OP>  // 0 = euclid, 1 = dot
 __global__ void __launch_bounds__(256)
 pairwise_kernel(const double* __restrict__ X, int64_t ld, int F, int N, double* __restrict__ out,
-                int64_t ldo) {
+                int64_t ldo, int row_begin, int row_end) {
+  const bool rect = row_begin >= 0;
   const int bi = blockIdx.y, bj = blockIdx.x;
-  if (bj < bi) return;  // symmetric: upper tiles only, mirrored on write
+  if (!rect && bj < bi) return;  // symmetric: upper tiles only, mirrored on write
   __shared__ double sA[PW_FK][PW_TILE];
   __shared__ double sB[PW_FK][PW_TILE];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int i0 = bi * PW_TILE, j0 = bj * PW_TILE;
+  const int i0 = (rect ? row_begin : 0) + bi * PW_TILE, j0 = bj * PW_TILE;
+  const int i_end = rect ? row_end : N;
   double acc[4][4];
 #pragma unroll
   for (int u = 0; u < 4; ++u)
@@ -40,7 +46,7 @@ pairwise_kernel(const double* __restrict__ X, int64_t ld, int F, int N, double* 
     for (int e = threadIdx.x; e < PW_FK * PW_TILE; e += 256) {
       const int ff = e / PW_TILE, c = e - ff * PW_TILE;
       const int f = f0 + ff;
-      sA[ff][c] = (f < F && i0 + c < N) ? X[(int64_t)f * ld + i0 + c] : 0.0;
+      sA[ff][c] = (f < F && i0 + c < i_end) ? X[(int64_t)f * ld + i0 + c] : 0.0;
       sB[ff][c] = (f < F && j0 + c < N) ? X[(int64_t)f * ld + j0 + c] : 0.0;
     }
     __syncthreads();
@@ -69,10 +75,14 @@ pairwise_kernel(const double* __restrict__ X, int64_t ld, int F, int N, double* 
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       const int i = i0 + ty * 4 + u, j = j0 + tx * 4 + v;
-      if (i < N && j < N) {
+      if (i < i_end && j < N) {
         const double r = (OP == 0) ? sqrt(acc[u][v]) : acc[u][v];
-        out[(int64_t)i * ldo + j] = r;
-        if (bi != bj) out[(int64_t)j * ldo + i] = r;
+        if (rect) {
+          out[(int64_t)(i - row_begin) * ldo + j] = r;
+        } else {
+          out[(int64_t)i * ldo + j] = r;
+          if (bi != bj) out[(int64_t)j * ldo + i] = r;
+        }
       }
     }
 }
@@ -170,9 +180,25 @@ extern "C" int scrna_pairwise_f64(const double* X, int64_t ld, int F, int N, int
   if (t > 65535) return SCRNA_ERR_UNSUPPORTED;
   dim3 grid(t, t);
   if (op == 0)
-    pairwise_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(X, ld, F, N, out, ldo);
+    pairwise_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(X, ld, F, N, out, ldo, -1, -1);
   else
-    pairwise_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(X, ld, F, N, out, ldo);
+    pairwise_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(X, ld, F, N, out, ldo, -1, -1);
+  return last_launch_status();
+}
+
+extern "C" int scrna_pairwise_rows_f64(const double* X, int64_t ld, int F, int N, int op, int row_begin, int row_end,
+                                       double* out, int64_t ldo, void* stream) {
+  if (!X || !out || F <= 0 || N <= 0 || ld < N || ldo < N || (op != 0 && op != 1) || row_begin < 0 ||
+      row_end > N || row_begin > row_end)
+    return SCRNA_ERR_BADARG;
+  if (row_begin == row_end) return SCRNA_OK;
+  const int tx = (int)ceil_div(N, PW_TILE), ty = (int)ceil_div(row_end - row_begin, PW_TILE);
+  if (tx > 65535 || ty > 65535) return SCRNA_ERR_UNSUPPORTED;
+  dim3 grid(tx, ty);
+  if (op == 0)
+    pairwise_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(X, ld, F, N, out, ldo, row_begin, row_end);
+  else
+    pairwise_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(X, ld, F, N, out, ldo, row_begin, row_end);
   return last_launch_status();
 }
 

@@ -121,6 +121,13 @@ class TorchDistComm:
     def all_reduce(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
 
+    def all_gather_rows(self, full, bounds):
+        """`full` (rows x cols) holds this rank's row block bounds[rank]; afterwards every rank holds all blocks."""
+        for src, (r0, r1) in enumerate(bounds):
+            if r1 > r0:
+                self.dist.broadcast(full[r0:r1], src=self.dist.get_global_rank(self.group, src)
+                                    if self.group is not None else src, group=self.group)
+
 
 class NmfResult:
     def __init__(self, G, C, n_iter, flags, violations=None, errors=None):

@@ -60,14 +60,27 @@ class Sc3Ops:
         return t.zeros(shape, dtype=dtype or t.float64, device=self.dev)
 
     # ---- a12 distances ------------------------------------------------------------------------------
-    def distances(self, X, metric="euclidean"):
+    def _pairwise(self, Xd, F, N, op, out, comm=None):
+        """N x N pairwise kernel; with `comm` (world > 1) each rank computes a contiguous block of rows and the
+        blocks are all-gathered (SC3 distances shard by row blocks, X replicated)."""
+        if comm is None or comm.world <= 1:
+            self._call("scrna_pairwise_f64", Xd, N, F, N, op, out, N, self._s())
+            return out
+        from .nmf_solver import shard_bounds
+        r0, r1 = shard_bounds(N, comm.world, comm.rank)
+        block = out[r0:r1]                       # contiguous rows of the final matrix
+        self._call("scrna_pairwise_rows_f64", Xd, N, F, N, op, r0, r1, block, N, self._s())
+        bounds = [shard_bounds(N, comm.world, r) for r in range(comm.world)]
+        comm.all_gather_rows(out, bounds)
+        return out
+
+    def distances(self, X, metric="euclidean", comm=None):
         """X: genes x cells (numpy or device fp64) -> device n x n distance matrix."""
         Xd = self.to_device(X)
         F, N = Xd.shape
         out = self.empty(N, N)
         if metric == "euclidean":
-            self._call("scrna_pairwise_f64", Xd, N, F, N, 0, out, N, self._s())
-            return out
+            return self._pairwise(Xd, F, N, 0, out, comm)
         if metric == "pearson":
             work = Xd.clone()
         elif metric == "spearman":
@@ -81,8 +94,7 @@ class Sc3Ops:
             raise ValueError("metric must be 'euclidean', 'pearson' or 'spearman' (got %r)" % (metric,))
         mean = self.empty(N)
         self._call("scrna_col_center_f64", work, N, F, N, mean, self._s(), launches=2)
-        G = self.empty(N, N)
-        self._call("scrna_pairwise_f64", work, N, F, N, 1, G, N, self._s())
+        G = self._pairwise(work, F, N, 1, self.empty(N, N), comm)
         self._call("scrna_corr_epilogue_f64", G, N, N, F, out, N, self._s())
         return out
 

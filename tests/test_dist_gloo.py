@@ -90,3 +90,32 @@ def test_shard_bounds_cover_and_balance():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _gather_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from scrna_b200.nmf_solver import TorchDistComm, shard_bounds
+        n = 37
+        full = torch.arange(n * n, dtype=torch.float64).reshape(n, n)
+        mine = torch.full((n, n), -1.0, dtype=torch.float64)
+        bounds = [shard_bounds(n, world, r) for r in range(world)]
+        r0, r1 = bounds[rank]
+        mine[r0:r1] = full[r0:r1]            # this rank's row block of the distance matrix
+        TorchDistComm().all_gather_rows(mine, bounds)
+        ret[rank] = bool(torch.equal(mine, full))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sc3_distance_row_blocks_all_gather_world2():
+    """SC3 distances shard by row blocks: the all-gather that assembles D on every rank."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gather_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert [ret[r] for r in range(world)] == [True, True]

@@ -117,6 +117,24 @@ def test_block_jacobi_vs_lapack(ops, n, kind):
     assert np.linalg.norm(M.T @ (M @ V) - V * (vals[:c] ** 2)) / (s[0] ** 2) < 1e-9
 
 
+@pytest.mark.parametrize("op", [0, 1])
+def test_pairwise_row_blocks_bit_identical(ops, op):
+    """Row-block launches (the multi-GPU sharding of the distance stage) reproduce the rows of the full
+    symmetric launch bit for bit."""
+    import scrna_b200._lib as L
+    torch = ops.torch
+    rng = np.random.RandomState(4)
+    F, N = 300, 333
+    X = ops.to_device(rng.poisson(3.0, size=(F, N)).astype(np.float64) + rng.rand(F, N))
+    full = ops.empty(N, N)
+    L.call("scrna_pairwise_f64", X, N, F, N, op, full, N, ops._s())
+    parts = ops.zeros(N, N)
+    for r0, r1 in ((0, 111), (111, 222), (222, 333)):
+        L.call("scrna_pairwise_rows_f64", X, N, F, N, op, r0, r1, parts[r0:r1], N, ops._s())
+    torch.cuda.synchronize()
+    assert torch.equal(full, parts)
+
+
 def test_kmeans_labelings_vs_reference(ops, sc3g):
     k, pc = int(sc3g["k"]), [int(v) for v in sc3g["pc_range"]]
     V = sc3g["V_euclidean_pca"]

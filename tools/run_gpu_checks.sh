@@ -1,2 +1,3 @@
-python -m pytest tests/test_gpu_sc3.py tests/test_gpu_pipeline.py -m gpu -x -q 2>&1 | tail -4 > gpurun_out/t_gpu.log
-timeout 300 python tools/svd_bench.py 2000 8000 > gpurun_out/svd_plain.log 2>&1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/t_gpu.log
+python bench.py > gpurun_out/bench_s4.json 2> gpurun_out/bench_s4.err
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
