@@ -29,8 +29,8 @@ GENES, CELLS, K = 20000, 100000, 8
 L1, L2 = 7.5, 2.5                      # alpha=10, l1_ratio=.75 (cmd_source.py:34-35)
 METRIC = "NMF MU iters/s (20k genes x 100k cells, k=8)"
 # dram__bytes_read.sum + dram__bytes_write.sum per sweep launch from the committed `ncu --set full` captures of
-# the default workload on one GPU (profiles/r01_sweep_full_raw.csv, profiles/r01_tcgen05_sweep_k32_full_raw.csv)
-NCU_TRAFFIC = {"simt": 8.003e9 + 0.03e9, "tcgen05": 8.033e9 + 0.023e9}
+# the default workload on one GPU (profiles/r01_sweep_full_raw.csv, profiles/r01_tcgen05_sweep_k8_full_raw.csv)
+NCU_TRAFFIC = {"simt": 8.003e9 + 0.03e9, "tcgen05": 8.018e9 + 0.014e9}
 UNIT = "iterations/s"
 E2E_ITERS = 100                        # NmfClustering.apply default max_iter (nmf_clustering.py:20)
 CPU_SAMPLE_CELLS = 10000
