@@ -14,9 +14,9 @@
 //
 // Blocking.  Columns are grouped in blocks of 32; a round pairs the blocks (round-robin tournament) and for
 // every pair (I, J), independently:
-//   1. gram   : G = [W_I; W_J] . [W_I; W_J]^T                 (64 x 64, reduction over n, split partials)
+//   1. gram   : G = [W_I; W_J] . [W_I; W_J]^T                 (64 x 64, reduction over n, split partials; DMMA)
 //   2. eigen  : two-sided cyclic Jacobi on G in shared memory  -> U (64 x 64 orthogonal), G.U = U.diag
-//   3. apply  : [W_I; W_J] <- U^T . [W_I; W_J]                  (64 x 64 times 64 x n)
+//   3. apply  : [W_I; W_J] <- U^T . [W_I; W_J]                  (64 x 64 times 64 x n; DMMA)
 // A sweep is nblk-1 rounds; traffic per sweep drops from 32 n^3 to n^3 bytes and the work is two GEMMs.
 #include "common.cuh"
 
@@ -33,62 +33,71 @@ __device__ __forceinline__ void bj_pair(int m, int round, int i, int& p, int& q)
   if (p > q) { const int t = p; p = q; q = t; }
 }
 
+// FP64 tensor-core MMA (DMMA): D(8x8) += A(8x4, row) . B(4x8, col).  Lane l holds A[l/4][l%4], B[l%4][l/4] and
+// D[l/4][2(l%4) .. +1].  Same peak as the DFMA pipe on B200 (18.5 vs 17 TFMA/s measured,
+// profiles/r01_dmma_rate_microbench.txt) but 8 FMA per lane for two operand doubles: the 4x4 register-tile
+// DFMA kernels were shared-memory bound (ncu: 70 % LSU wavefronts, fp64 pipe 28 %).
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
 // ---- 1. pair Gram partials: part[pair][split][64*64] ------------------------------------------------
-// The 64 x 32 chunk is staged TRANSPOSED ([k][row], pitch 66) so that a thread's four rows / four columns are
-// two 128-bit shared-memory loads each.  (An 8 x 8 register-tile variant measured slower: 2.8 vs 4.3 TFMA/s,
-// its 186 registers leave one CTA per SM and nothing to overlap the staging with.)
-constexpr int BJ_TP = BJ_P + 2;
-constexpr int BJ_KC = 32;         // reduction chunk of the Gram kernel
+// 64 rows x 32 k staged row-major (pitch 36: fragment loads are 2-way = optimal for 64-bit, staging stores
+// conflict-free); 8 warps, each a 16 x 32 slice of the 64 x 64 Gram as 2 x 4 DMMA tiles.
+constexpr int BJ_KC = 32;          // reduction chunk of the Gram kernel
+constexpr int BJ_GP = BJ_KC + 4;   // pitch of the staged chunk
 __global__ void __launch_bounds__(256)
 bj_gram_kernel(const double* __restrict__ W, int64_t ld, int n, int nblk, int m, int round, int nsplit,
                double* __restrict__ part) {
   int p, q;
   bj_pair(m, round, blockIdx.x, p, q);
   if (q >= nblk) return;  // bye
-  __shared__ __align__(16) double tile[BJ_KC][BJ_TP];
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  __shared__ double tile[BJ_P * BJ_GP];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wr = warp >> 1, wc = warp & 1;        // rows 16 wr .., columns 32 wc ..
+  const int lr = lane >> 2, lk = lane & 3;
   const int per = (int)(((int64_t)n + nsplit - 1) / nsplit);
   const int c_begin = blockIdx.y * per;
   const int c_end = min(n, c_begin + per);
-  double acc[4][4];
+  double acc[2][4][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   for (int c0 = c_begin; c0 < c_end; c0 += BJ_KC) {
     __syncthreads();
     for (int e = tid; e < BJ_P * BJ_KC; e += 256) {
       const int r = e / BJ_KC, c = e % BJ_KC;
       const int64_t row = (r < BJ_B) ? (int64_t)p * BJ_B + r : (int64_t)q * BJ_B + (r - BJ_B);
-      tile[c][r] = (c0 + c < c_end) ? W[row * ld + c0 + c] : 0.0;
+      tile[r * BJ_GP + c] = (c0 + c < c_end) ? W[row * ld + c0 + c] : 0.0;
     }
     __syncthreads();
-#pragma unroll 8
-    for (int kk = 0; kk < BJ_KC; ++kk) {
-      // thread (ty, tx) owns rows {2ty, 2ty+1, 32+2ty, 33+2ty} x columns {2tx, 2tx+1, 32+2tx, 33+2tx}: the 16
-      // lanes of a half-warp read 256 contiguous bytes per load (no half-used shared-memory wavefronts)
-      const double2 a01 = *reinterpret_cast<const double2*>(&tile[kk][2 * ty]);
-      const double2 a23 = *reinterpret_cast<const double2*>(&tile[kk][32 + 2 * ty]);
-      const double2 b01 = *reinterpret_cast<const double2*>(&tile[kk][2 * tx]);
-      const double2 b23 = *reinterpret_cast<const double2*>(&tile[kk][32 + 2 * tx]);
-      const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-      const double b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+    for (int kk = 0; kk < BJ_KC / 4; ++kk) {
+      double a[2], b[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < 2; ++i) a[i] = tile[(16 * wr + 8 * i + lr) * BJ_GP + 4 * kk + lk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = tile[(32 * wc + 8 * j + lr) * BJ_GP + 4 * kk + lk];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
     }
   }
   double* out = part + ((int64_t)blockIdx.x * nsplit + blockIdx.y) * (BJ_P * BJ_P);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      out[((i < 2 ? 0 : 32 - 2) + 2 * ty + i) * BJ_P + (j < 2 ? 0 : 32 - 2) + 2 * tx + j] = acc[i][j];
+      *reinterpret_cast<double2*>(&out[(16 * wr + 8 * i + lr) * BJ_P + 32 * wc + 8 * j + 2 * lk]) =
+          make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
 // ---- 2. eigenvectors of the 64 x 64 pair Gram: U[pair][64*64] (row-major, G.U = U.diag) ---------------
-constexpr int BJ_ET = 1024;  // threads of the eigen kernel: one CTA per pair, at most one pair per SM
+constexpr int BJ_ET = 512;   // threads of the eigen kernel: one CTA per pair, three pairs resident per SM
 __global__ void __launch_bounds__(BJ_ET)
 bj_eigen_kernel(const double* __restrict__ part, int nsplit, int nblk, int m, int round, double tol,
                 double null_sq, double* __restrict__ Uout, int* __restrict__ rotated) {
@@ -182,6 +191,11 @@ bj_eigen_kernel(const double* __restrict__ part, int nsplit, int nblk, int m, in
 }
 
 // ---- 3. apply: rows [I; J] of W  <-  U^T . rows -----------------------------------------------------
+// One CTA = 128 columns of the pair's 64 rows; 8 warps, each a 32 x 32 output slice as 4 x 4 DMMA tiles
+// (8 operand loads per 16 DMMA).  U is staged as [s][r] (pitch 72), the rows as [s][col] (pitch 136).
+constexpr int BJ_AC = 128;
+constexpr int BJ_UP = BJ_P + 8;
+constexpr int BJ_AP = BJ_AC + 8;
 __global__ void __launch_bounds__(256)
 bj_apply_kernel(double* __restrict__ W, int64_t ld, int n, int nblk, int m, int round,
                 const double* __restrict__ Uall) {
@@ -189,44 +203,52 @@ bj_apply_kernel(double* __restrict__ W, int64_t ld, int n, int nblk, int m, int 
   bj_pair(m, round, blockIdx.x, p, q);
   if (q >= nblk) return;
   extern __shared__ __align__(16) double bj_smem[];
-  double* Us = bj_smem;                 // [s][r]   64 x 66
-  double* T = Us + BJ_P * BJ_TP;        // [s][col] 64 x 66
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const int c0 = blockIdx.y * BJ_P;
+  double* Us = bj_smem;                 // [s][r]   64 x 72
+  double* T = Us + BJ_P * BJ_UP;        // [s][col] 64 x 136
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wr = warp >> 2, wc = warp & 3;        // rows 32 wr .., columns 32 wc ..
+  const int lr = lane >> 2, lk = lane & 3;
+  const int c0 = blockIdx.y * BJ_AC;
   const double* Ug = Uall + (int64_t)blockIdx.x * (BJ_P * BJ_P);
-  for (int e = tid; e < BJ_P * BJ_P; e += 256) {
-    const int s = e / BJ_P, c = e % BJ_P;
-    Us[s * BJ_TP + c] = Ug[e];
+  for (int e = tid; e < BJ_P * BJ_P; e += 256) Us[(e / BJ_P) * BJ_UP + (e % BJ_P)] = Ug[e];
+  for (int e = tid; e < BJ_P * BJ_AC; e += 256) {
+    const int s = e / BJ_AC, c = e % BJ_AC;
     const int64_t row = (s < BJ_B) ? (int64_t)p * BJ_B + s : (int64_t)q * BJ_B + (s - BJ_B);
-    T[s * BJ_TP + c] = (c0 + c < n) ? W[row * ld + c0 + c] : 0.0;
+    T[s * BJ_AP + c] = (c0 + c < n) ? W[row * ld + c0 + c] : 0.0;
   }
   __syncthreads();
-  double acc[4][4];
+  double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-#pragma unroll 8
-  for (int s = 0; s < BJ_P; ++s) {
-    const double2 a01 = *reinterpret_cast<const double2*>(&Us[s * BJ_TP + 2 * ty]);
-    const double2 a23 = *reinterpret_cast<const double2*>(&Us[s * BJ_TP + 32 + 2 * ty]);
-    const double2 b01 = *reinterpret_cast<const double2*>(&T[s * BJ_TP + 2 * tx]);
-    const double2 b23 = *reinterpret_cast<const double2*>(&T[s * BJ_TP + 32 + 2 * tx]);
-    const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-    const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
+  for (int kk = 0; kk < BJ_P / 4; ++kk) {
+    const int s = 4 * kk + lk;
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = Us[s * BJ_UP + 32 * wr + 8 * i + lr];   // A[r][s] = U[s][r]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = T[s * BJ_AP + 32 * wc + 8 * j + lr];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int r = (i < 2 ? 0 : 32 - 2) + 2 * ty + i;
+    const int r = 32 * wr + 8 * i + lr;
     const int64_t row = (r < BJ_B) ? (int64_t)p * BJ_B + r : (int64_t)q * BJ_B + (r - BJ_B);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = c0 + (j < 2 ? 0 : 32 - 2) + 2 * tx + j;
-      if (c < n) W[row * ld + c] = acc[i][j];
+      const int c = c0 + 32 * wc + 8 * j + 2 * lk;
+      double* wp = W + row * ld + c;
+      if (c + 1 < n && ((reinterpret_cast<uintptr_t>(wp) & 15) == 0)) {
+        *reinterpret_cast<double2*>(wp) = make_double2(acc[i][j][0], acc[i][j][1]);
+      } else {
+        if (c < n) wp[0] = acc[i][j][0];
+        if (c + 1 < n) wp[1] = acc[i][j][1];
+      }
     }
   }
 }
@@ -277,7 +299,7 @@ extern "C" int scrna_bjacobi_sweep_f64(double* W, int64_t ld, int n, double tol,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static bool attr = false;
   const size_t smem = 2 * (size_t)BJ_P * BJ_LD * sizeof(double);
-  const size_t smem_apply = 2 * (size_t)BJ_P * BJ_TP * sizeof(double);
+  const size_t smem_apply = ((size_t)BJ_P * BJ_UP + (size_t)BJ_P * BJ_AP) * sizeof(double);
   if (!attr) {
     cudaFuncSetAttribute(bj_eigen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_apply);
@@ -286,7 +308,7 @@ extern "C" int scrna_bjacobi_sweep_f64(double* W, int64_t ld, int n, double tol,
   for (int round = 0; round < m - 1; ++round) {
     bj_gram_kernel<<<dim3(pairs, nsplit), 256, 0, st>>>(W, ld, n, nblk, m, round, nsplit, part);
     bj_eigen_kernel<<<pairs, BJ_ET, smem, st>>>(part, nsplit, nblk, m, round, tol, null_sq, U, rotated);
-    bj_apply_kernel<<<dim3(pairs, (unsigned)ceil_div(n, BJ_P)), 256, smem_apply, st>>>(W, ld, n, nblk, m, round, U);
+    bj_apply_kernel<<<dim3(pairs, (unsigned)ceil_div(n, BJ_AC)), 256, smem_apply, st>>>(W, ld, n, nblk, m, round, U);
   }
   return last_launch_status();
 }
