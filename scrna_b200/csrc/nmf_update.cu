@@ -278,6 +278,146 @@ update_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
   }
 }
 
+// ---- MU update, tiled: 32 rows x 8 component groups per CTA -----------------------------------------------
+// The row-per-thread kernel above keeps the CD sweep's sequential order; for the multiplicative update nothing
+// is sequential, and at rank 32-64 (136 KB of shared memory, four warps per SM) or on a small shard (fewer
+// CTAs than SMs) it was latency bound: 0.4 ms per half step at k=50.  Here a CTA owns tiles of 32 rows, thread
+// (r, grp) owns CPT = ceil(k/8) components of row r: the split-partial sums, the k x k denominators (the old
+// row broadcast from shared memory) and the writes are spread over 8x more threads, ~60 KB of shared memory
+// leaves three CTAs per SM, and the Gram of the new rows accumulates in registers across the CTA's tiles.
+constexpr int UT_ROWS = 32;
+constexpr int UT_GROUPS = 8;
+constexpr int UT_THREADS = UT_ROWS * UT_GROUPS;
+constexpr int UT_LD = UT_ROWS + 1;
+constexpr int UT_MAXCPT = SCRNA_MAX_K / UT_GROUPS;           // 8
+constexpr int UT_MAXG = SCRNA_MAX_K * SCRNA_MAX_K / UT_THREADS;  // 16 Gram entries per thread
+
+__global__ void __launch_bounds__(UT_THREADS)
+update_mu_tiled_kernel(double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
+                       const double* __restrict__ num, const float* __restrict__ num_parts, int nsplit,
+                       const double* __restrict__ gram, double l1, double l2, float* __restrict__ S32,
+                       float* __restrict__ T32, float* __restrict__ TC32, double* __restrict__ viol_part,
+                       double* __restrict__ gram_part_out, NmfCtrl* __restrict__ ctrl) {
+  if (ctrl_done(ctrl)) return;
+  extern __shared__ double smem[];
+  double* sg = smem;                      // kp x kp Gram of the other factor
+  double* sw = sg + kp * kp;              // k x UT_LD old row entries
+  double* sv = sw + (size_t)k * UT_LD;    // k x UT_LD new row entries
+  __shared__ int snan;
+  const int tid = threadIdx.x, r = tid & (UT_ROWS - 1), grp = tid >> 5;
+  const int cpt = (k + UT_GROUPS - 1) / UT_GROUPS;
+  const int t_begin = grp * cpt, t_end = min(k, t_begin + cpt);
+  for (int o = tid; o < kp * kp; o += UT_THREADS) sg[o] = gram[o];
+  if (tid == 0) snan = 0;
+  double gacc[UT_MAXG];
+#pragma unroll
+  for (int i = 0; i < UT_MAXG; ++i) gacc[i] = 0.0;
+  bool nan_seen = false;
+  const int64_t ntiles = (rows + UT_ROWS - 1) / UT_ROWS;
+  const int64_t stride = (int64_t)kp * ld;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row = tile * UT_ROWS + r;
+    const bool live = row < rows;
+    __syncthreads();  // previous tile's Gram accumulation has read sv
+    double nv[UT_MAXCPT];
+#pragma unroll
+    for (int u = 0; u < UT_MAXCPT; ++u) nv[u] = 0.0;
+    for (int u = 0; u < UT_MAXCPT; ++u) {
+      const int t = t_begin + u;
+      if (u < cpt && t < t_end) {
+        const int64_t e = (int64_t)t * ld + row;
+        sw[t * UT_LD + r] = live ? F64[e] : 0.0;
+        if (live) {
+          if (num_parts) {  // fixed-order fp64 sum of the sweep's split partials
+            double a = 0.0;
+#pragma unroll 4
+            for (int p = 0; p < nsplit; ++p) a += (double)num_parts[(int64_t)p * stride + e];
+            nv[u] = a;
+          } else {
+            nv[u] = num[e];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // F *= num / (F.gram + l1 + l2*F): denominators of this thread's components, q in order
+    double den[UT_MAXCPT];
+#pragma unroll
+    for (int u = 0; u < UT_MAXCPT; ++u) den[u] = 0.0;
+    for (int q = 0; q < k; ++q) {
+      const double wq = sw[q * UT_LD + r];
+      const double* gq = sg + q * kp + t_begin;
+#pragma unroll
+      for (int u = 0; u < UT_MAXCPT; ++u)
+        if (u < cpt && t_begin + u < t_end) den[u] += wq * gq[u];
+    }
+#pragma unroll
+    for (int u = 0; u < UT_MAXCPT; ++u) {
+      const int t = t_begin + u;
+      if (u < cpt && t < t_end) {
+        const double w = sw[t * UT_LD + r];
+        double d = den[u];
+        if (l1 > 0.0) d += l1;
+        if (l2 > 0.0) d = d + l2 * w;
+        if (d == 0.0) d = (double)kEpsMU;
+        const double v = live ? w * (nv[u] / d) : 0.0;
+        sv[t * UT_LD + r] = v;
+        if (live) {
+          nan_seen |= (v != v);
+          const int64_t e = (int64_t)t * ld + row;
+          F64[e] = v;
+          if (T32) T32[e] = (float)v;
+          if (S32) S32[row * kp + t] = (float)v;
+          if (TC32) {
+            float* base = TC32 + ((row >> 2) * 2 * kp) * 4 + (row & 3);
+            const float h = __uint_as_float(__float_as_uint((float)v) & 0xffffe000u);
+            base[t * 4] = h;
+            base[(kp + t) * 4] = __uint_as_float(__float_as_uint((float)(v - (double)h)) & 0xffffe000u);
+          }
+        }
+      }
+    }
+    if (live && S32)  // padding components of the row-major shadow stay zero
+      for (int t = k + grp; t < kp; t += UT_GROUPS) S32[row * kp + t] = 0.f;
+    __syncthreads();
+    if (gram_part_out) {
+      // Gram of the tile's new rows, entries o = tid, tid + 256, ... (rows of sv are conflict-free by pitch)
+#pragma unroll
+      for (int i = 0; i < UT_MAXG; ++i) {
+        const int o = tid + i * UT_THREADS;
+        if (o < kp * kp) {
+          const int a = o / kp, b = o - a * kp;
+          if (a < k && b < k) {
+            const double* ra = sv + a * UT_LD;
+            const double* rb = sv + b * UT_LD;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+            for (int q = 0; q < UT_ROWS; q += 2) {
+              a0 = fma(ra[q], rb[q], a0);
+              a1 = fma(ra[q + 1], rb[q + 1], a1);
+            }
+            gacc[i] += a0 + a1;
+          }
+        }
+      }
+    }
+  }
+  if (nan_seen) snan = 1;
+  __syncthreads();
+  if (tid == 0) {
+    if (viol_part) viol_part[blockIdx.x] = 0.0;
+    if (snan && ctrl) atomicOr(&ctrl->flags, SCRNA_FLAG_NAN);
+  }
+  if (gram_part_out) {
+    double* gp = gram_part_out + (int64_t)blockIdx.x * kp * kp;
+#pragma unroll
+    for (int i = 0; i < UT_MAXG; ++i) {
+      const int o = tid + i * UT_THREADS;
+      if (o < kp * kp) gp[o] = gacc[i];
+    }
+  }
+}
+
 // fp64 component-major master (kp x ld) -> fp32 row-major shadow (rows x kp) [+ component-major shadow]
 __global__ void shadows_kernel(const double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kp,
                                float* __restrict__ S32, float* __restrict__ T32) {
@@ -421,7 +561,17 @@ extern "C" int scrna_nmf_gram(const double* F, int64_t rs, int64_t cs, int64_t r
   return last_launch_status();
 }
 
-extern "C" int scrna_nmf_update_blocks(int64_t rows) { return (int)ceil_div(rows, UPD_THREADS); }
+static int tiled_blocks(int64_t rows) {
+  int64_t b = ceil_div(rows, UT_ROWS);
+  const int64_t cap = 3 * (int64_t)num_sms();
+  return (int)(b < cap ? b : cap);
+}
+
+// number of per-block slots (violation sums, Gram partials) an update launch may write
+extern "C" int scrna_nmf_update_blocks(int64_t rows) {
+  const int a = (int)ceil_div(rows, UPD_THREADS), b = tiled_blocks(rows);
+  return a > b ? a : b;
+}
 
 extern "C" int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t rows, int k, int kp,
                                 const double* num, const float* num_parts, int nsplit, const double* gram,
@@ -432,19 +582,26 @@ extern "C" int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t row
       k > kp || kp > SCRNA_MAX_K || (kp & 3) || (gram_out && !gram_partials))
     return SCRNA_ERR_BADARG;
   const size_t smem = ((size_t)kp * kp + 2 * (size_t)k * UPD_LD) * sizeof(double);
-  const int nblk = (int)ceil_div(rows, UPD_THREADS);
+  int nblk = (int)ceil_div(rows, UPD_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
   if (!attr_set) {
+    cudaFuncSetAttribute(update_mu_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(update_kernel<SCRNA_SOLVER_MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(update_kernel<SCRNA_SOLVER_CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  if (solver == SCRNA_SOLVER_MU)
+  if (solver == SCRNA_SOLVER_MU && kp < 48) {
+    // ranks up to 32: the row-per-thread kernel has more loads in flight per thread and measured faster
     update_kernel<SCRNA_SOLVER_MU><<<nblk, UPD_THREADS, smem, st>>>(F64, ld, rows, k, kp, num, num_parts, nsplit, gram,
                                                                   l1, l2, perms, perm_stride, perm_offset, S32, T32,
                                                                   TC32, viol_part, gram_partials, (NmfCtrl*)ctrl);
-  else if (solver == SCRNA_SOLVER_CD)
+  } else if (solver == SCRNA_SOLVER_MU) {
+    nblk = tiled_blocks(rows);
+    const size_t smem_t = ((size_t)kp * kp + 2 * (size_t)k * UT_LD) * sizeof(double);
+    update_mu_tiled_kernel<<<nblk, UT_THREADS, smem_t, st>>>(F64, ld, rows, k, kp, num, num_parts, nsplit, gram, l1, l2,
+                                                            S32, T32, TC32, viol_part, gram_partials, (NmfCtrl*)ctrl);
+  } else if (solver == SCRNA_SOLVER_CD)
     update_kernel<SCRNA_SOLVER_CD><<<nblk, UPD_THREADS, smem, st>>>(F64, ld, rows, k, kp, num, num_parts, nsplit, gram,
                                                                   l1, l2, perms, perm_stride, perm_offset, S32, T32,
                                                                   TC32, viol_part, gram_partials, (NmfCtrl*)ctrl);

@@ -140,13 +140,14 @@ def test_sweeps_match_fp64_products(kernels, g, n, k, transpose_copy):
 
 
 @pytest.mark.parametrize("fused_parts", [False, True])
-@pytest.mark.parametrize("solver", ["cd", "mu"])
-def test_single_update_matches_oracle(kernels, solver, fused_parts):
-    """One half step with exact fp64 inputs: the epilogue alone, compared at fp64 rounding level."""
+@pytest.mark.parametrize("solver,rank", [("cd", (7, 8)), ("mu", (7, 8)), ("mu", (50, 64)), ("cd", (50, 64)), ("mu", (33, 48))])
+def test_single_update_matches_oracle(kernels, solver, fused_parts, rank):
+    """One half step with exact fp64 inputs: the epilogue alone, compared at fp64 rounding level (row-per-thread
+    kernel for CD and MU up to rank 32, tiled kernel for MU above)."""
     import scrna_b200._lib as L
     torch = kernels.torch
     rng = np.random.RandomState(11)
-    rows, k, kp, ld = 777, 7, 8, 800
+    rows, (k, kp), ld = 777, rank, 800
     W = np.abs(rng.randn(rows, k))
     W[rng.rand(rows, k) < 0.25] = 0.0
     A = np.abs(rng.randn(50, k))

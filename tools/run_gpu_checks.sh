@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_sc3.py tests/test_gpu_pipeline.py -m gpu -x -q 2>&1 | tail -6 > gpurun_out/t_gpu.log
-timeout 600 python tools/svd_bench.py 4000 8000 20000 > gpurun_out/svd_plain.log 2>&1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/t_gpu.log
+python tools/kbench.py --k 8 32 50 --tc auto --out gpurun_out/kbench_upd2.json > gpurun_out/kbench_upd2.log 2>&1
