@@ -315,6 +315,10 @@ def run_gpu(args):
     ms = float(tms.item())
     value = args.steps / (ms / 1e3)
 
+    # ||X - G.C||_F over all shards after the warm-up + timed iterations: identical initial factors at every N,
+    # so this number must agree between the 1-, 2-, 4- and 8-GPU runs (a cross-check of the sharded path)
+    fro_after = slv.frobenius_error()
+
     # dominant kernel: the X sweep (wtx_partial_kernel<8,4,8>), two launches per iteration
     sweep_ms = [a.elapsed_time(b) for a, b, _ in sweeps]
     sweep_bytes = [nb for _, _, nb in sweeps]
@@ -408,6 +412,7 @@ def run_gpu(args):
                        "parallelism": "cells sharded x%d, one all-reduce of %d fp64 per iteration"
                                       % (world, k * genes + k * k + 4) if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "frobenius_error_after_timed_steps": fro_after,
             "cpu_baseline": cpu_baseline, "sc3_consensus": sc3,
         }
         emit(line)

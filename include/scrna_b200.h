@@ -251,7 +251,8 @@ int scrna_gather_vectors_f64(const double* VT, int64_t ld, int n, const int32_t*
 /* K13 at scale: block one-sided Jacobi on N = M^T (sc3_svd_block.cu).  W (n_pad x ld, n_pad = 32 *
  * scrna_bjacobi_blocks(n), rows >= n zero) starts as a copy of M; one call = one sweep (all block pairs once:
  * pair Gram -> 64 x 64 eigenproblem in shared memory -> rotation of the 64 rows, two GEMM-shaped kernels);
- * `rotated` += block pairs that still had a coupling above 1e-11 (0 after a sweep == converged).  Afterwards
+ * `rotated` += block pairs that still had a coupling above 1e-8 (0 after a sweep == converged: the rotations
+ * of that sweep were applied and, by quadratic convergence, leave couplings at rounding level).  Afterwards
  * row j of W is sigma_j * v_j: scrna_row_sqnorm_f64 gives sigma^2, scrna_gather_scaled_f64 the unit vectors.
  * Columns whose squared norm is <= null_sq (numerically null: pass (1e-12 sigma_max)^2) are never rotated.
  * work: scrna_bjacobi_work_elems(n) doubles.  n > 32. */

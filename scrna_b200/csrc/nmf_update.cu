@@ -591,8 +591,10 @@ extern "C" int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t row
     cudaFuncSetAttribute(update_kernel<SCRNA_SOLVER_CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  if (solver == SCRNA_SOLVER_MU && kp < 48) {
-    // ranks up to 32: the row-per-thread kernel has more loads in flight per thread and measured faster
+  if (solver == SCRNA_SOLVER_MU && kp < 48 && rows >= 2 * (int64_t)num_sms() * UPD_THREADS) {
+    // ranks up to 32 on long factors: the row-per-thread kernel has more loads in flight per thread and measured
+    // faster; short factors (the replicated gene factor, a cell shard on 4-8 GPUs) leave it with fewer CTAs than
+    // SMs and go to the tiled kernel below
     update_kernel<SCRNA_SOLVER_MU><<<nblk, UPD_THREADS, smem, st>>>(F64, ld, rows, k, kp, num, num_parts, nsplit, gram,
                                                                   l1, l2, perms, perm_stride, perm_offset, S32, T32,
                                                                   TC32, viol_part, gram_partials, (NmfCtrl*)ctrl);
