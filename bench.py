@@ -49,10 +49,14 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------------
 # synthetic counts: restatement of simulation.generate_counts with torch RNGs
 # ---------------------------------------------------------------------------------------------
+CELL_BLOCK = 12500   # cells per generator block: shard boundaries at N = 1, 2, 4, 8 fall on block boundaries
+
+
 def synth_counts(torch, device, genes, cell_begin, cell_end, seed=1234, clusters=8, rows_per_band=2000):
     """genes x (cell_end-cell_begin) fp32 NB counts on `device`, leading dimension padded to 32.
-    Gene-level parameters depend on `seed` only (identical on every rank); cell-level draws are
-    keyed by the absolute cell index range so that shards tile the same global matrix."""
+    Gene-level parameters depend on `seed` only (identical on every rank); cell-level draws are made per block
+    of CELL_BLOCK cells from a generator keyed by the block's absolute index, so that every sharding tiles the
+    SAME global matrix (the N-GPU runs factorise identical data)."""
     n = cell_end - cell_begin
     ldx = ((n + 31) // 32) * 32
     gg = torch.Generator(device=device)
@@ -64,18 +68,22 @@ def synth_counts(torch, device, genes, cell_begin, cell_end, seed=1234, clusters
     lfc = (1.0 + 0.5 * torch.randn((genes, clusters), device=device, generator=gg)) * torch.where(
         torch.rand((genes, clusters), device=device, generator=gg) < 0.5, -1.0, 1.0)
     fold = torch.where(de, torch.pow(2.0, lfc), torch.ones_like(lfc))                   # genes x clusters
-    gc = torch.Generator(device=device)
-    gc.manual_seed(seed * 7919 + cell_begin + 1)
-    label = torch.randint(0, clusters, (n,), device=device, generator=gc)
-    size = torch.pow(2.0, 0.5 * torch.randn(n, device=device, generator=gc))
     X = torch.zeros((genes, ldx), dtype=torch.float32, device=device)
-    for r0 in range(0, genes, rows_per_band):
-        r1 = min(genes, r0 + rows_per_band)
-        mu = mean[r0:r1, None] * fold[r0:r1][:, label] * size[None, :]
-        # NB(n=10, p=10/(10+mu)) drawn as Poisson(Gamma(10, rate=10/mu))
-        shape = torch.full_like(mu, 10.0)
-        lam = torch._standard_gamma(shape, generator=gc) * (mu / 10.0)
-        X[r0:r1, :n] = torch.poisson(lam, generator=gc)
+    for blk in range(cell_begin // CELL_BLOCK, (cell_end + CELL_BLOCK - 1) // CELL_BLOCK):
+        b0 = blk * CELL_BLOCK
+        gc = torch.Generator(device=device)
+        gc.manual_seed(seed * 7919 + blk + 1)
+        label = torch.randint(0, clusters, (CELL_BLOCK,), device=device, generator=gc)
+        size = torch.pow(2.0, 0.5 * torch.randn(CELL_BLOCK, device=device, generator=gc))
+        lo, hi = max(cell_begin, b0), min(cell_end, b0 + CELL_BLOCK)   # the part of the block this shard owns
+        for r0 in range(0, genes, rows_per_band):
+            r1 = min(genes, r0 + rows_per_band)
+            mu = mean[r0:r1, None] * fold[r0:r1][:, label] * size[None, :]
+            # NB(n=10, p=10/(10+mu)) drawn as Poisson(Gamma(10, rate=10/mu))
+            shape = torch.full_like(mu, 10.0)
+            lam = torch._standard_gamma(shape, generator=gc) * (mu / 10.0)
+            cnt = torch.poisson(lam, generator=gc)
+            X[r0:r1, lo - cell_begin: hi - cell_begin] = cnt[:, lo - b0: hi - b0]
     return X, n
 
 
