@@ -1,4 +1,4 @@
-// Tensor-core X sweep for sm_100a (tcgen05 + TMEM + bulk-TMA), ranks kp = 16 .. 64.
+// Tensor-core X sweep for sm_100a (tcgen05 + TMEM + tensor-map TMA), ranks kp = 16 .. 64.
 //
 //   part[s][t][j] = sum_{i in row span s} F[i][t] * X[i][j]          (F^T . X, same contract as K3)
 //

@@ -40,3 +40,22 @@ def test_source_to_target_to_sc3_labels_match_reference(kernels, default_sim, go
         s3.set_consensus_clustering(partial(sc.consensus_clustering, n_components=k))
         s3.apply()
         np.testing.assert_array_equal(s3.cluster_labels, g_s[key])
+
+
+def test_source_model_pickles_like_the_reference(kernels, default_sim):
+    """cmd_source.py:208-212 stores the fitted source object with np.savez(src=nmf) (a pickle) and cmd_target.py
+    :188-189 loads it back: the object must carry no device state and keep the reference's attribute names."""
+    import pickle
+    from scrna_b200 import NmfClustering_initW
+    nmf = NmfClustering_initW(default_sim["src"][:300, :200], default_sim["gene_ids"][:300], 7,
+                              default_sim["src_labels"][:200])
+    k = len(np.unique(default_sim["src_labels"][:200]))
+    nmf.apply(k=k, alpha=10., l1=0.75, max_iter=200, rel_err=1e-3)
+    nmf.cell_filter_list = None   # as the reference does before saving (lambdas do not pickle)
+    nmf.gene_filter_list = None
+    nmf.data_transf = None
+    back = pickle.loads(pickle.dumps(nmf))
+    for name in ("dictionary", "data_matrix", "cluster_labels", "pp_data", "remain_gene_inds", "remain_cell_inds",
+                 "gene_ids", "num_cluster"):
+        a, b = getattr(nmf, name), getattr(back, name)
+        assert np.array_equal(np.asarray(a), np.asarray(b)), name
