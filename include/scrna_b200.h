@@ -265,6 +265,12 @@ int scrna_bjacobi_sweep_f64(double* W, int64_t ld, int n, double tol, double nul
 int scrna_gather_scaled_f64(const double* W, int64_t ld, int n, const int32_t* order, const double* scale, int c,
                             double* out, int64_t ldo, void* stream);
 
+/* out[r][i] = W[order[r]][i] * scale[r], r < c (c x n): with scale_r = sqrt(s_r) / sigma_r the Gram of these rows
+ * (scrna_pairwise_f64 op 1) is V.diag(s).V^T, the matrix sc3_clustering_impl.py:196-203 rebuilds from the kept
+ * components. */
+int scrna_gather_rows_scaled_f64(const double* W, int64_t ld, int n, const int32_t* order, const double* scale, int c,
+                                 double* out, int64_t ldo, void* stream);
+
 /* K14-K17 k-means as sklearn KMeans(init='k-means++', algorithm='lloyd') runs it
  * (sc3_clustering_impl.py:215-217).  state: 8 doubles {tol, potential, shift_tot, inertia, changed, n_empty}. */
 int scrna_km_prepare(const double* V, int64_t ldv, int n, int d, double* X, int64_t ldx, double* xsq,

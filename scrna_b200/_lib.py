@@ -77,6 +77,7 @@ _SIGNATURES = {
     "scrna_bjacobi_work_elems": [c_int],
     "scrna_bjacobi_sweep_f64": [c_ptr, c_i64, c_int, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr],
     "scrna_gather_scaled_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr],
+    "scrna_gather_rows_scaled_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr],
     "scrna_km_prepare": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_kmeans_pp": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_dbl, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                         c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],

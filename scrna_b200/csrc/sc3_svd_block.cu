@@ -265,9 +265,26 @@ __global__ void bj_gather_kernel(const double* __restrict__ W, int64_t ld, int n
   out[(int64_t)i * ldo + r] = W[(int64_t)src * ld + i] * scale[src];
 }
 
+// out[r][i] = W[order[r]][i] * scale[r]  (c x n: the kept vectors as scaled ROWS, for V.diag(s).V^T as a Gram)
+__global__ void bj_gather_rows_kernel(const double* __restrict__ W, int64_t ld, int n, const int* __restrict__ order,
+                                      const double* __restrict__ scale, int c, double* __restrict__ out, int64_t ldo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (i >= n || r >= c) return;
+  out[(int64_t)r * ldo + i] = W[(int64_t)order[r] * ld + i] * scale[r];
+}
+
 }  // namespace scrna
 
 using namespace scrna;
+
+extern "C" int scrna_gather_rows_scaled_f64(const double* W, int64_t ld, int n, const int32_t* order,
+                                            const double* scale, int c, double* out, int64_t ldo, void* stream) {
+  if (!W || !order || !scale || !out || n <= 0 || c <= 0 || ldo < n) return SCRNA_ERR_BADARG;
+  bj_gather_rows_kernel<<<dim3((unsigned)ceil_div(n, 256), c), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      W, ld, n, order, scale, c, out, ldo);
+  return last_launch_status();
+}
 
 extern "C" int scrna_bjacobi_blocks(int n) { return (int)ceil_div(n, BJ_B); }
 

@@ -92,7 +92,10 @@ def transformations(dm, components=5, method='pca'):
     V, vals = ops.right_singular_vectors(M, components)
     vecs = V.cpu().numpy()
     vals = vals / np.sqrt(np.max((1, num_cells - 1)))
-    rebuilt = vecs.dot(np.diag(vals[:components]).dot(vecs.T))
+    if ops._last is not None:
+        rebuilt = ops.rebuilt_matrix(vals[:components]).cpu().numpy()     # n x n Gram on the device
+    else:
+        rebuilt = vecs.dot(np.diag(vals[:components]).dot(vecs.T))         # n <= 64
     return rebuilt, _remember(vecs, V)
 
 

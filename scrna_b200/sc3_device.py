@@ -121,6 +121,7 @@ class Sc3Ops:
         the unblocked kernel."""
         t = self.torch
         n = M.shape[0]
+        self._last = None
         if blocked is None:
             blocked = n > 64
         if blocked:
@@ -180,7 +181,23 @@ class Sc3Ops:
         sc = t.from_numpy(inv).to(self.dev)
         V = self.empty(n, c)
         self._call("scrna_gather_scaled_f64", W, n, n, od, sc, c, V, c, self._s())
+        self._last = (W, od, inv[order[:c]], vals[order][:c])   # for rebuilt_matrix()
         return V, vals[order]
+
+    def rebuilt_matrix(self, weights):
+        """vecs . diag(weights) . vecs^T of the vectors just computed by the block solver (the first return value of
+        the reference's `transformations`, sc3_clustering_impl.py:196-203) as a Gram on the device: rows
+        sqrt(w_r) v_r, then the pairwise dot kernel -- instead of an n x c x n product on the host."""
+        t = self.torch
+        W, od, inv, _ = self._last
+        n = W.shape[1]
+        c = od.numel()
+        w = np.sqrt(np.maximum(np.asarray(weights, dtype=np.float64)[:c], 0.0)) * inv
+        Yt = self.empty(c, n)
+        self._call("scrna_gather_rows_scaled_f64", W, n, n, od, t.from_numpy(w).to(self.dev), c, Yt, n, self._s())
+        out = self.empty(n, n)
+        self._call("scrna_pairwise_f64", Yt, n, c, n, 1, out, n, self._s())
+        return out
 
     # ---- a14 k-means ----------------------------------------------------------------------------------
     def kmeans(self, V, d, k, draws, n_init=10, max_iter=10000):

@@ -67,6 +67,8 @@ def test_transformations_vs_reference(ops, sc3g, metric, method):
     sgn = np.sign((V * ref).sum(axis=0))
     np.testing.assert_allclose(V * sgn, ref, rtol=0, atol=1e-8)
     assert rebuilt.shape == D.shape
+    vals_ref = np.linalg.svd(Mref, compute_uv=False)[:c] / np.sqrt(max(1, D.shape[0] - 1))
+    np.testing.assert_allclose(rebuilt, (ref * vals_ref) @ ref.T, rtol=0, atol=1e-7 * vals_ref[0])
     from scrna_b200.sc3_device import default_ops
     assert default_ops().jacobi_sweeps < 30
 
