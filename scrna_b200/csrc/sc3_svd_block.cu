@@ -54,11 +54,12 @@ bj_gram_kernel(const double* __restrict__ W, int64_t ld, int n, int nblk, int m,
   int p, q;
   bj_pair(m, round, blockIdx.x, p, q);
   if (q >= nblk) return;  // bye
-  __shared__ double tile[BJ_P * BJ_GP];
+  __shared__ __align__(16) double tile[2 * BJ_P * BJ_GP];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wr = warp >> 1, wc = warp & 1;        // rows 16 wr .., columns 32 wc ..
   const int lr = lane >> 2, lk = lane & 3;
-  const int per = (int)(((int64_t)n + nsplit - 1) / nsplit);
+  int per = (int)(((int64_t)n + nsplit - 1) / nsplit);
+  per += per & 1;   // even spans: 16-byte staging units never straddle two splits
   const int c_begin = blockIdx.y * per;
   const int c_end = min(n, c_begin + per);
   double acc[2][4][2];
@@ -66,26 +67,54 @@ bj_gram_kernel(const double* __restrict__ W, int64_t ld, int n, int nblk, int m,
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  // double-buffered staging: 16-byte cp.async when the rows allow it (even n, ld, span start), else plain loads
+  const bool vec = ((n | (int)(ld & 1) | c_begin) & 1) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  auto stage = [&](int c0, double* T) {
+    if (vec) {
+      const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(T);
+      for (int e = tid; e < BJ_P * (BJ_KC / 2); e += 256) {
+        const int r = e / (BJ_KC / 2), u = e % (BJ_KC / 2);
+        const int c = c0 + 2 * u;
+        const int64_t row = (r < BJ_B) ? (int64_t)p * BJ_B + r : (int64_t)q * BJ_B + (r - BJ_B);
+        const bool ok = c < c_end;   // n and the spans are even: a unit is wholly inside or outside
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tbase + (uint32_t)(r * BJ_GP + 2 * u) * 8u),
+                     "l"(W + row * ld + (ok ? c : 0)), "r"(ok ? 16u : 0u)
+                     : "memory");
+      }
+    } else {
+      for (int e = tid; e < BJ_P * BJ_KC; e += 256) {
+        const int r = e / BJ_KC, c = e % BJ_KC;
+        const int64_t row = (r < BJ_B) ? (int64_t)p * BJ_B + r : (int64_t)q * BJ_B + (r - BJ_B);
+        T[r * BJ_GP + c] = (c0 + c < c_end) ? W[row * ld + c0 + c] : 0.0;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if (c_begin < c_end) stage(c_begin, tile);
   for (int c0 = c_begin; c0 < c_end; c0 += BJ_KC) {
-    __syncthreads();
-    for (int e = tid; e < BJ_P * BJ_KC; e += 256) {
-      const int r = e / BJ_KC, c = e % BJ_KC;
-      const int64_t row = (r < BJ_B) ? (int64_t)p * BJ_B + r : (int64_t)q * BJ_B + (r - BJ_B);
-      tile[r * BJ_GP + c] = (c0 + c < c_end) ? W[row * ld + c0 + c] : 0.0;
+    const double* T = tile + buf * (BJ_P * BJ_GP);
+    if (c0 + BJ_KC < c_end) {
+      stage(c0 + BJ_KC, tile + (buf ^ 1) * (BJ_P * BJ_GP));
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < BJ_KC / 4; ++kk) {
       double a[2], b[4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) a[i] = tile[(16 * wr + 8 * i + lr) * BJ_GP + 4 * kk + lk];
+      for (int i = 0; i < 2; ++i) a[i] = T[(16 * wr + 8 * i + lr) * BJ_GP + 4 * kk + lk];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = tile[(32 * wc + 8 * j + lr) * BJ_GP + 4 * kk + lk];
+      for (int j = 0; j < 4; ++j) b[j] = T[(32 * wc + 8 * j + lr) * BJ_GP + 4 * kk + lk];
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
     }
+    __syncthreads();  // done with this buffer before the next iteration refills it
+    buf ^= 1;
   }
   double* out = part + ((int64_t)blockIdx.x * nsplit + blockIdx.y) * (BJ_P * BJ_P);
 #pragma unroll
