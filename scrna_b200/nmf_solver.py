@@ -195,9 +195,9 @@ class NmfSolver:
         if self.tc:
             self.Gtc = t.zeros(kernels.tc_shadow_elems(g, kp), dtype=f32, device=dev)
             self.Ctc = t.zeros(kernels.tc_shadow_elems(n, kp), dtype=f32, device=dev)
-            self.SA = kernels.wtx_tc_splits(n, self.gcols, kp)
+            self.SA = int(os.environ.get("SCRNA_B200_TC_SA", 0)) or kernels.wtx_tc_splits(n, self.gcols, kp)
             self.PA = t.zeros((self.SA, kp, ldg), dtype=f32, device=dev)
-            self.SB = kernels.wtx_tc_splits(g, X.ncols, kp)
+            self.SB = int(os.environ.get("SCRNA_B200_TC_SB", 0)) or kernels.wtx_tc_splits(g, X.ncols, kp)
         elif self.XT is not None:
             self.Gtc = self.Ctc = None
             self.SA = kernels.wtx_splits(n, self.gcols, kp)
