@@ -135,14 +135,23 @@ class ClockSampler:
 # CPU legs (the only place bench.py executes oracle/): the reference's arithmetic on the host cores
 # ---------------------------------------------------------------------------------------------
 def cpu_mu_iterations(X64, W0, H0, iters):
-    """Times `iters` iterations of the oracle's sklearn-MU restatement (numpy/BLAS, all host threads)."""
+    """Times `iters` iterations of the oracle's sklearn-MU restatement (numpy/BLAS, all host threads:
+    torchrun exports OMP_NUM_THREADS=1 to its workers, so the BLAS pools are widened explicitly)."""
     from oracle import nmf_oracle as no
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        limiter = None
     W, H = W0.copy(), H0.copy()
     t0 = time.perf_counter()
     for _ in range(iters):
         W = no.mu_update_w(X64, W, H, L1, L2)
         H = no.mu_update_h(X64, W, H, L1, L2)
-    return (time.perf_counter() - t0) / iters
+    dt = (time.perf_counter() - t0) / iters
+    if limiter is not None:
+        limiter.restore_original_limits()
+    return dt
 
 
 def cpu_sample(sample_cells, seed=1234):
