@@ -24,8 +24,13 @@ class SC3Clustering(AbstractClustering):
     sub_sample = None
     consensus_mode = None
 
-    def __init__(self, data, gene_ids=None, pc_range=[4, 10], sub_sample=True, consensus_mode=0):
+    def __init__(self, data, gene_ids=None, pc_range=[4, 10], sub_sample=True, consensus_mode=0, comm=None):
+        """`comm` (opt-in, not in the reference): a TorchDistComm of the ranks that all call apply() on the same
+        data; the k-means fits of the ensemble -- independent units -- are then dealt round-robin over the ranks
+        and their label vectors all-reduced.  Needs clustering callables that advertise
+        `supports_skip` (this package's intermediate_kmeans_clustering does)."""
         super(SC3Clustering, self).__init__(data, gene_ids=gene_ids)
+        self.comm = comm if (comm is not None and comm.world > 1) else None
         self.dists_list = []
         self.dimred_list = []
         self.intermediate_clustering_list = []
@@ -70,6 +75,24 @@ class SC3Clustering(AbstractClustering):
             range_inds = np.random.permutation(range_inds)[:15]
 
         n = self.remain_cell_inds.size
+        # ---- the ensemble: one labeling per (clustering, transformation, d), in the reference's loop order ----
+        fits = []       # (cluster index, transformation index, labels or None when another rank owns the fit)
+        fit_idx = 0
+        for ci, cluster in enumerate(self.intermediate_clustering_list):
+            shardable = self.comm is not None and getattr(getattr(cluster, "func", cluster), "supports_skip", False)
+            for t in range(len(transf)):
+                _, deigv = transf[t]
+                for d in range_inds:
+                    Xd = deigv[:, 0:d].reshape((deigv.shape[0], d))
+                    if shardable and fit_idx % self.comm.world != self.comm.rank:
+                        cluster(Xd, _skip=True)          # stay on the RNG stream; the owner computes the fit
+                        fits.append((ci, t, None))
+                    else:
+                        fits.append((ci, t, np.array(cluster(Xd))))
+                    fit_idx += 1
+        if self.comm is not None and any(l is None for _, _, l in fits):
+            self._gather_labels(fits, n)
+
         cnt = 0.
         device_acc = self._uses_device_consensus()
         if device_acc:
@@ -77,12 +100,13 @@ class SC3Clustering(AbstractClustering):
             M = ops.coassoc_new(n)
         else:
             consensus2 = np.zeros((n, n))
-        for cluster in self.intermediate_clustering_list:
+        pos = 0
+        for ci in range(len(self.intermediate_clustering_list)):
             for t in range(len(transf)):
-                _, deigv = transf[t]
                 labels = []
-                for d in range_inds:
-                    labels.append(cluster(deigv[:, 0:d].reshape((deigv.shape[0], d))))
+                for _ in range_inds:
+                    labels.append(fits[pos][2])
+                    pos += 1
                     if self.consensus_mode == 0:
                         if device_acc:
                             ops.coassoc_add(M, np.array(labels[-1]))
@@ -98,3 +122,20 @@ class SC3Clustering(AbstractClustering):
         else:
             consensus2 /= cnt
         self.cluster_labels, self.dists = self.consensus_clustering(consensus2)
+
+    def _gather_labels(self, fits, n):
+        """All-reduce (sum) of an (n_fits x cells) label table in which every rank filled the rows it owns."""
+        import torch
+        table = np.zeros((len(fits), n), dtype=np.int64)
+        for i, (_, _, l) in enumerate(fits):
+            if l is not None:
+                table[i] = np.asarray(l).reshape(-1)
+        use_cuda = torch.cuda.is_available() and self.comm.dist.get_backend(self.comm.group) == "nccl"
+        tt = torch.from_numpy(table)
+        if use_cuda:
+            tt = tt.cuda()
+        self.comm.all_reduce(tt)
+        table = tt.cpu().numpy()
+        for i, (ci, t, l) in enumerate(fits):
+            if l is None:
+                fits[i] = (ci, t, table[i].copy())

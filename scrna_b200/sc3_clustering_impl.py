@@ -107,21 +107,30 @@ def kmeans_draws(k, n_init=10):
     return np.random.random_sample(n_init * per)
 
 
-def intermediate_kmeans_clustering(X, k=5, n_init=10, max_iter=10000, init='k-means++'):
+def intermediate_kmeans_clustering(X, k=5, n_init=10, max_iter=10000, init='k-means++', _skip=False):
     """cells x 1 labels of KMeans(n_clusters=k, n_init, max_iter, init='k-means++') on the cells x d matrix
-    (scRNA/sc3_clustering_impl.py:206-219)."""
+    (scRNA/sc3_clustering_impl.py:206-219).
+
+    `_skip=True` (used by SC3Clustering when the k-means ensemble is distributed over several GPUs)
+    only consumes the fit's random draws from the global NumPy RNG -- so that every rank stays on the reference's
+    RNG stream -- and returns None: the fit itself runs on another rank."""
     if init != 'k-means++':
         raise NotImplementedError("only init='k-means++' (the reference's default and only use) is on the device")
+    draws = kmeans_draws(k, n_init)
+    if _skip:
+        return None
     ops = _ops()
     X = np.asarray(X)
     n, d = X.shape
     dev = _lookup(X)
     V = dev if dev is not None else ops.to_device(np.ascontiguousarray(X, dtype=np.float64))
-    draws = kmeans_draws(k, n_init)
     # V may be a column-slice view of the resident vectors: its row stride is the leading dimension
     labels = ops.kmeans(V, d, k, draws, n_init=n_init, max_iter=max_iter)
     assert labels.size == n
     return labels
+
+
+intermediate_kmeans_clustering.supports_skip = True
 
 
 def build_consensus_matrix(X):

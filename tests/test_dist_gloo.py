@@ -119,3 +119,68 @@ def test_sc3_distance_row_blocks_all_gather_world2():
     ret = mgr.dict()
     mp.spawn(_gather_worker, args=(world, port, ret), nprocs=world, join=True)
     assert [ret[r] for r in range(world)] == [True, True]
+
+
+def _sc3_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.cluster.hierarchy as spc
+        from scipy.spatial.distance import pdist, squareform
+        from scrna_b200.nmf_solver import TorchDistComm
+        from scrna_b200.sc3_clustering import SC3Clustering
+        rng = np.random.RandomState(3)
+        X = np.concatenate([rng.randn(30, 20) + 4 * rng.randn(30, 1) for _ in range(3)], axis=1)   # 30 genes x 60 cells
+
+        def dist_fn(data, gene_ids):
+            return squareform(pdist(data.T))
+
+        def dimred(D):
+            return None, np.linalg.svd(D - D.mean(axis=0))[2].T[:, :6]
+
+        def cluster(V, _skip=False):
+            # stand-in k-means (test infrastructure): consumes the global RNG like a real fit would
+            u = np.random.random_sample(3)
+            if _skip:
+                return None
+            return (V[:, 0] > np.quantile(V[:, 0], 0.3 + 0.4 * u[0])).astype(int) + (V[:, -1] > 0).astype(int)
+        cluster.supports_skip = True
+
+        def consensus(labels):
+            l = np.asarray(labels).reshape(-1)
+            return (l[:, None] == l[None, :]).astype(float)
+
+        def final(C):
+            Z = spc.complete(pdist(C))
+            return spc.cut_tree(Z, n_clusters=3).reshape(-1), squareform(pdist(C))
+
+        def run(comm):
+            np.random.seed(11)
+            sc3 = SC3Clustering(X, np.arange(30), pc_range=[2, 6], sub_sample=True, consensus_mode=0, comm=comm)
+            sc3.add_distance_calculation(dist_fn)
+            sc3.add_dimred_calculation(dimred)
+            sc3.add_intermediate_clustering(cluster)
+            sc3.set_build_consensus_matrix(consensus)
+            sc3.set_consensus_clustering(final)
+            sc3.apply()
+            return sc3.cluster_labels, sc3.dists, np.random.random_sample()
+
+        ref_labels, ref_dists, ref_next = run(None)
+        got_labels, got_dists, got_next = run(TorchDistComm())
+        ret[rank] = bool(np.array_equal(ref_labels, got_labels) and np.array_equal(ref_dists, got_dists)
+                         and ref_next == got_next)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sc3_kmeans_ensemble_sharded_world2():
+    """The k-means fits of the SC3 ensemble dealt over two ranks: same consensus, same labels and the same position
+    on the global RNG stream as the single-process run (skipped fits still consume their draws)."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sc3_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert [ret[r] for r in range(world)] == [True, True]
