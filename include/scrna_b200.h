@@ -302,6 +302,17 @@ int scrna_consensus_scale(const int32_t* M, int64_t ldm, int n, double cnt, doub
 int scrna_hclust_complete(double* D, int64_t ld, int n, int n_clusters, int32_t* labels, double* Z, double* merges,
                           int32_t* iwork, void* stream);
 
+/* ---- evaluation: kernel-target alignment (scRNA/utils.py:66-152; cmd_target.py:254-260 picks the mixture by it) --
+ * After Kx = X^T X (scrna_pairwise_f64 op 1): rowstats gives the row sums and the diagonal; align returns
+ * out = {<Kxn, Kyn>, <Kxn, Kxn>, <Kyn, Kyn>} for Kn_ij = (K_ij - mean_i - mean_j + tot) * scale_i * scale_j with the
+ * label kernel Ky_ij = [l_i == l_j] formed on the fly (centring / normalisation are closed forms of the row means,
+ * the reference uses dense n^3 products).  partials: 3 * scrna_kta_blocks() doubles. */
+int scrna_kta_blocks(void);
+int scrna_kta_rowstats_f64(const double* K, int64_t ld, int n, double* rowsum, double* diag, void* stream);
+int scrna_kta_align_f64(const double* K, int64_t ld, int n, const int32_t* labels, const double* mean_x,
+                        const double* scale_x, double tot_x, const double* mean_y, const double* scale_y, double tot_y,
+                        double* partials, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,9 @@ _SIGNATURES = {
     "scrna_bjacobi_sweep_f64": [c_ptr, c_i64, c_int, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr],
     "scrna_gather_scaled_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr],
     "scrna_gather_rows_scaled_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr],
+    "scrna_kta_blocks": [],
+    "scrna_kta_rowstats_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr],
+    "scrna_kta_align_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr],
     "scrna_km_prepare": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_kmeans_pp": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_dbl, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                         c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
@@ -97,7 +100,7 @@ _SIGNATURES = {
 _VALUE_RETURNING = {"scrna_abi_version", "scrna_nmf_xht_splits", "scrna_nmf_wtx_splits", "scrna_nmf_gram_blocks",
                     "scrna_nmf_update_blocks", "scrna_residual_blocks", "scrna_nmf_tc_supported", "scrna_nmf_wtx_tc_splits",
                     "scrna_nmf_tc_shadow_elems", "scrna_bjacobi_blocks", "scrna_bjacobi_splits",
-                    "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems"}
+                    "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems", "scrna_kta_blocks"}
 
 
 _RETURNS_I64 = {"scrna_nmf_tc_shadow_elems", "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems"}

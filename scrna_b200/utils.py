@@ -74,3 +74,65 @@ def get_matching_gene_inds(src_gene_ids, trg_gene_ids):
             inds2.append(first_src[s])
     assert len(inds1) > 0
     return np.asarray(inds1, dtype=int), np.asarray(inds2, dtype=int)
+
+
+def unsupervised_acc_kta(X, labels, kernel='linear', param=1.0, center=True, normalize=True):
+    """Kernel-target alignment of the cells' linear kernel with the label kernel (scRNA/utils.py:134-152; the score
+    cmd_target.py:254-260 maximises over the mixtures).  The linear kernel X^T X is the device Gram
+    (scrna_pairwise_f64), centring / normalisation / the three Frobenius products are two O(n^2) device passes
+    (csrc/eval_kta.cu) instead of the reference's dense n^3 products.
+
+    `kernel='rbf'` is not on the device.  A labeling with a single cluster makes the centred label kernel vanish
+    and the reference returns rounding noise; 0.0 is returned here."""
+    if kernel != 'linear':
+        raise NotImplementedError("only the linear kernel (the reference CLI's choice) is implemented on the device")
+    from . import _lib
+    from .sc3_device import default_ops
+    ops = default_ops()
+    t = ops.torch
+    X = np.asarray(X, dtype=np.float64)
+    labels = np.asarray(labels).astype(np.int64).reshape(-1)
+    n = X.shape[1]
+    if labels.size != n:
+        raise ValueError("one label per cell expected")
+    Xd = ops.to_device(X)
+    K = ops.empty(n, n)
+    ops._call("scrna_pairwise_f64", Xd, n, X.shape[0], n, 1, K, n, ops._s())
+    rowsum, diag = ops.empty(n), ops.empty(n)
+    ops._call("scrna_kta_rowstats_f64", K, n, n, rowsum, diag, ops._s())
+    rs, dg = rowsum.cpu().numpy(), diag.cpu().numpy()
+
+    def params(rowsum_, diag_):
+        """(row means, scales, total mean) of a kernel given its row sums and diagonal; None scales = the
+        normalisation is numerically unstable (normalize_kernel's identity fallback, utils.py:71-73)."""
+        if center:
+            mean, tot = rowsum_ / float(n), rowsum_.sum() / float(n) ** 2
+        else:
+            mean, tot = np.zeros(n), 0.0
+        d = diag_ - 2.0 * mean + tot
+        if not normalize:
+            return mean, np.ones(n), tot, d
+        with np.errstate(all='ignore'):
+            a = np.sqrt(d)
+        if np.any(np.isnan(a)) or np.any(np.isinf(a)) or np.any(np.abs(a) <= 1e-16):
+            return mean, None, tot, d
+        return mean, 1.0 / a, tot, d
+
+    counts = np.bincount(labels, minlength=int(labels.max()) + 1).astype(np.float64)
+    mx, bx, tx, dx = params(rs, dg)
+    my, by, ty, dy = params(counts[labels], np.ones(n))
+    if bx is None or by is None:
+        # identity fallback: only the diagonals of the (centred) kernels survive -- O(n) on the host
+        kx = dx if bx is None else np.ones(n)
+        ky = dy if by is None else np.ones(n)
+        den = np.sqrt((kx * kx).sum() * (ky * ky).sum())
+        return float((kx * ky).sum() / den) if den > 0 else 0.0
+    dev = lambda a: t.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(ops.dev)
+    part = ops.empty(3 * _lib.call("scrna_kta_blocks"))
+    out = ops.empty(3)
+    lab32 = t.from_numpy(labels.astype(np.int32)).to(ops.dev)
+    ops._call("scrna_kta_align_f64", K, n, n, lab32, dev(mx), dev(bx), float(tx), dev(my), dev(by), float(ty), part,
+              out, ops._s(), launches=2)
+    sxy, sxx, syy = out.cpu().numpy()
+    den = np.sqrt(sxx * syy)
+    return float(sxy / den) if den > 0 else 0.0

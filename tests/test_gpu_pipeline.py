@@ -59,3 +59,19 @@ def test_source_model_pickles_like_the_reference(kernels, default_sim):
                  "gene_ids", "num_cluster"):
         a, b = getattr(nmf, name), getattr(back, name)
         assert np.array_equal(np.asarray(a), np.asarray(b)), name
+
+
+@pytest.mark.parametrize("name", ["trg_true", "src_300", "trg_log", "trg_random_labels", "one_cluster"])
+def test_kta_score_vs_reference_golden(kernels, golden, name):
+    """Row f3: unsupervised_acc_kta on the device against the reference's own scores (tests/golden/kta.npz)."""
+    from scrna_b200.utils import unsupervised_acc_kta
+    g = golden("kta")
+    X, lab = g[name + "_X"].astype(np.float64), g[name + "_labels"]
+    for c in (True, False):
+        for nrm in (True, False):
+            if name == "one_cluster" and c:
+                assert unsupervised_acc_kta(X, lab, center=c, normalize=nrm) == 0.0   # reference: rounding noise
+                continue
+            ref = float(g["%s_kta_c%d_n%d" % (name, c, nrm)])
+            got = unsupervised_acc_kta(X, lab, center=c, normalize=nrm)
+            assert abs(got - ref) < 1e-10, (name, c, nrm, got, ref)
