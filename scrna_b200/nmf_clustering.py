@@ -216,10 +216,6 @@ class DaNmfClustering(NmfClustering):
         trg_data = trg_data[inds1, :]
         assert np.all(src_gene_ids == self.gene_ids)
         assert self.src.dictionary is not None  # source data should always be pre-processed
-        if calc_transferability:
-            raise NotImplementedError('calc_transferability (utils.get_transferability_score) is evaluation '
-                                      'code outside the B200 hot path (SURVEY.md §8f, row f4)')
-
         W = np.ascontiguousarray(self.src.dictionary[inds2, :], dtype=np.float64)
         k = W.shape[1]
         n_t = trg_data.shape[1]
@@ -233,6 +229,15 @@ class DaNmfClustering(NmfClustering):
         self.cluster_labels = labels                      # == np.argmax(H, axis=0)
         self.intermediate_model = (W, H, H2)
         self.reject = self.calc_rejection(trg_data, W, H, H2, _session=sess)
+
+        if calc_transferability:   # nmf_clustering.py:175-183
+            from .utils import get_transferability_score
+            self.transferability_score, self.transferability_rand_scores, self.transferability_pvalue = \
+                get_transferability_score(W, H, trg_data, max_iter=max_iter)
+            self.transferability_percs = np.percentile(self.transferability_rand_scores, [25, 50, 75, 100])
+            self.reject.append(('Transfer_Percentiles', self.transferability_percs))
+            self.reject.append(('Transferability', self.transferability_score))
+            self.reject.append(('Transferability p-value', self.transferability_pvalue))
 
         assert reject_ratio < 1.  # rejection of 100% (or more) does not make any sense
         if reject_ratio > 0.:

@@ -1,8 +1,9 @@
 """Hot-path helpers with the reference's names and signatures (scRNA/utils.py:187-278).
 
-Only the functions on the north-star path live here: `get_transferred_data_matrix` (:187-230) and
-`get_matching_gene_inds` (:233-278).  KTA kernels, TSV loaders and the transferability score
-(:11-184) are evaluation / IO and out of scope.
+On the north-star path: `get_transferred_data_matrix` (:187-230) and `get_matching_gene_inds` (:233-278).
+"Next" rows of SURVEY.md §8f built on the same device kernels: `unsupervised_acc_kta` (:134-152, row f3) and
+`get_transferability_score` (:155-184, row f4).  TSV / npz loaders and the rbf kernel (:11-63, 108-124) are IO /
+unused by the CLI and stay out of scope.
 """
 import numpy as np
 
@@ -136,3 +137,41 @@ def unsupervised_acc_kta(X, labels, kernel='linear', param=1.0, center=True, nor
     sxy, sxx, syy = out.cpu().numpy()
     den = np.sqrt(sxx * syy)
     return float(sxy / den) if den > 0 else 0.0
+
+
+def get_transferability_score(W, H, trg_data, reps=100, alpha=0.0, l1=0.75, max_iter=100, rel_err=1e-3):
+    """Transferability of a source dictionary to a target data set (scRNA/utils.py:155-184; row f4 of SURVEY.md §8):
+    `reps` target solves with the dictionary's gene rows permuted (the "no transfer" error distribution), the
+    un-permuted solve, an NMF of the target itself (the best achievable error) and the error of the given (W, H).
+    Returns (score, percs, p_value) like the reference.
+
+    The target is uploaded once; every solve is the device path of `get_transferred_data_matrix` (K5-K7) and
+    draws, in the reference's order, `np.random.permutation(genes)` then `np.random.randn(k, n_t)` from the global
+    legacy RNG; the target NMF is `NmfClustering`'s solver with tol=1e-5 (its NNDSVDar init uses its own
+    RandomState(0), as in scikit-learn)."""
+    from .kernels import default_kernels
+    from .nmf_clustering import _fit_nmf
+    from .nmf_solver import DeviceMatrix
+    W = np.ascontiguousarray(W, dtype=np.float64)
+    trg_data = np.asarray(trg_data, dtype=np.float64)
+    dm = DeviceMatrix.from_host(trg_data, default_kernels())
+    errs = np.zeros((reps,))
+    for i in range(errs.size):
+        rand_gene_inds = np.random.permutation(W.shape[0])
+        _, _, _, errs[i] = get_transferred_data_matrix(W[rand_gene_inds, :], dm, max_iter=max_iter, rel_err=rel_err)
+    sess = TransferSession(W, dm)
+    _, _, _, err_nonpermuted = get_transferred_data_matrix(W, dm, max_iter=max_iter, rel_err=rel_err, _session=sess)
+
+    res = _fit_nmf(trg_data, W.shape[1], alpha, l1, max_iter, 0.00001, 'cd', 'host')
+    best = TransferSession(res.G, dm)
+    best._set_H(res.C)
+    err_best = best.l1_error()                      # sum|X - W_best.H_best| / size
+    sess._set_H(np.asarray(H, dtype=np.float64))
+    err_curr = sess.l1_error()                      # sum|X - W.H| / size
+    err_worst = np.max(errs)
+
+    errs[errs < err_best] = err_best
+    percs = 1.0 - (errs - err_best) / (err_worst - err_best)
+    score = 1.0 - np.max([err_curr - err_best, 0]) / (err_worst - err_best)
+    p_value = sum(errs < err_nonpermuted) / reps
+    return score, percs, p_value

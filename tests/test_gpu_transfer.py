@@ -113,3 +113,28 @@ def test_zero_dictionary_column_raises(kernels):
     X = rng.poisson(2.0, size=(40, 20)).astype(np.float64)
     with pytest.raises(Exception, match='DA target: division by zero.'):
         get_transferred_data_matrix(W, X)
+
+
+def test_transferability_score_vs_reference_golden(kernels, default_sim, golden):
+    """Row f4: utils.get_transferability_score (8 permuted-dictionary solves, the un-permuted solve, the target's own
+    NMF) against the reference's output for the same RNG seed (tests/golden/transferability.npz)."""
+    from scrna_b200.utils import get_transferability_score
+    g, gs = golden("transferability"), golden("nmf_source")
+    W = gs["initw_dictionary"].astype(np.float64)
+    np.random.seed(4)
+    score, percs, p_value = get_transferability_score(W, g["H"], default_sim["trg"], reps=8, max_iter=100)
+    assert abs(score - float(g["score"])) < 1e-4
+    np.testing.assert_allclose(percs, g["percs"], rtol=0, atol=1e-4)
+    assert p_value == float(g["p_value"])
+
+
+def test_get_mixed_data_with_transferability(kernels, default_sim, golden):
+    from scrna_b200 import NmfClustering_initW, DaNmfClustering
+    src = NmfClustering_initW(default_sim["src"], default_sim["gene_ids"], 7, default_sim["src_labels"])
+    src.apply(k=7, alpha=10., l1=0.75, max_iter=4000, rel_err=1e-3)
+    np.random.seed(1)
+    da = DaNmfClustering(src, default_sim["trg"].copy(), default_sim["gene_ids"], 7)
+    da.get_mixed_data(mix=0.5, calc_transferability=True, max_iter=20)
+    names = [n for n, _ in da.reject]
+    assert names[-3:] == ['Transfer_Percentiles', 'Transferability', 'Transferability p-value']
+    assert 0.0 <= da.transferability_score <= 1.0 and da.transferability_percs.shape == (4,)
