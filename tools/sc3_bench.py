@@ -12,7 +12,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from oracle import sc3_oracle as so
 from scrna_b200.sc3_device import Sc3Ops, kmeans_draw_count
 
 
@@ -88,6 +87,9 @@ def main():
         from sklearn.metrics import adjusted_rand_score
         row["ari_vs_simulated_labels"] = float(adjusted_rand_score(lab, glabels))
         if not args.no_cpu:
+            # CPU comparison leg (measurement tooling, like bench.py's cpu_baseline): the reference's scipy / sklearn
+            # calls as restated in oracle/ -- imported here only, never by the product
+            from oracle import sc3_oracle as so
             Dc = {}
             for m in ("euclidean", "pearson", "spearman"):
                 row["cpu"]["dist_" + m], Dc[m] = cpu_time(lambda: so.distances(X, m))
