@@ -324,3 +324,44 @@ def test_nmf_clustering_with_device_init(kernels, default_sim, golden):
     assert rel_fro(nmf.dictionary, g["nmf_W"]) < TOL_FACTOR
     assert rel_fro(nmf.data_matrix, g["nmf_H"]) < TOL_FACTOR
     np.testing.assert_array_equal(nmf.cluster_labels, g["nmf_labels"])
+
+
+def test_fixw_default_data_vs_reference_golden(kernels, default_sim, golden, sweep_path):
+    """NmfClustering_fixW (scRNA/nmf_clustering.py:92-130): two fixed-factor CD solves, against the reference's
+    own output (tests/golden/fixw.npz, written by tests/golden/make_golden_fixw.py)."""
+    from scrna_b200 import NmfClustering_fixW
+    g = golden("fixw")
+    nmf = NmfClustering_fixW(default_sim["src"], default_sim["gene_ids"], 7, default_sim["src_labels"])
+    nmf.apply(k=7, alpha=1.0, l1=0.75, max_iter=100, rel_err=1e-3)
+    assert rel_fro(nmf.dictionary, g["dictionary"]) < TOL_FACTOR
+    np.testing.assert_array_equal(np.asarray(nmf.data_matrix, dtype=np.float64), g["data_matrix"])
+    np.testing.assert_array_equal(nmf.cluster_labels, g["cluster_labels"])
+
+
+def test_nan_factors_raise_like_the_reference(kernels, default_sim):
+    """nmf_clustering.py:33-38: NaNs in a factor raise Exception('W contains NaNs ...') / ('H contains NaNs ...').
+    (With the CD solver a NaN entry is squashed to 0 by max(w - grad/hess, 0) -- in sklearn's sweep as in ours --
+    so the multiplicative update carries the NaN to the check.)"""
+    from scrna_b200 import NmfClustering
+    X = default_sim["src"][:60, :50]
+    W0 = np.abs(np.random.RandomState(0).randn(60, 3))
+    H0 = np.abs(np.random.RandomState(1).randn(3, 50))
+    W0[5, 1] = np.nan
+    nmf = NmfClustering(X, np.arange(60), 3)
+    with pytest.raises(Exception, match="contains NaNs"):
+        nmf.apply(k=3, max_iter=5, init=(W0, H0), solver='mu')
+
+
+def test_reject_ratio_fails_like_the_reference(kernels, default_sim, golden):
+    """nmf_clustering.py:196-197 slices with a float: the reference raises TypeError for reject_ratio > 0, so do we;
+    reject_ratio >= 1 trips the assertion (:190)."""
+    from scrna_b200 import NmfClustering_initW, DaNmfClustering
+    src = NmfClustering_initW(default_sim["src"][:200, :150], np.arange(200), 7, default_sim["src_labels"][:150])
+    k = len(np.unique(default_sim["src_labels"][:150]))
+    src.apply(k=k, alpha=10., l1=0.75, max_iter=50, rel_err=1e-3)
+    da = DaNmfClustering(src, default_sim["trg"][:200].copy(), np.arange(200), k)
+    np.random.seed(0)
+    with pytest.raises(TypeError):
+        da.get_mixed_data(mix=0.5, reject_ratio=0.2)
+    with pytest.raises(AssertionError):
+        da.get_mixed_data(mix=0.5, reject_ratio=1.0)
