@@ -11,26 +11,19 @@ import numpy as np
 
 
 class AbstractClustering(object):
-    cell_filter_list = None
-    gene_filter_list = None
-    data_transf = None
-    data = None
-    gene_ids = None
-    num_cells = -1
-    num_transcripts = -1
-    pp_data = None
-    cluster_labels = None
-    remain_cell_inds = None
-    remain_gene_inds = None
+    """Attributes (same names as the reference): data, gene_ids, num_transcripts, num_cells, the filter lists and
+    the transformation, and after pre_processing(): pp_data, remain_gene_inds, remain_cell_inds; subclasses fill
+    cluster_labels."""
 
     def __init__(self, data, gene_ids=None):
-        self.cell_filter_list = []
-        self.gene_filter_list = []
-        self.data_transf = _identity
-        self.data = np.array(data, dtype=np.float64)      # always a private fp64 copy
-        self.num_transcripts, self.num_cells = self.data.shape
-        self.gene_ids = np.arange(self.num_transcripts) if gene_ids is None else gene_ids
-        self.cluster_labels = np.zeros((self.num_cells, 1))
+        matrix = np.array(data, dtype=np.float64)          # always a private fp64 copy of genes x cells
+        n_genes, n_cells = matrix.shape
+        self.__dict__.update(
+            data=matrix, num_transcripts=n_genes, num_cells=n_cells,
+            gene_ids=np.arange(n_genes) if gene_ids is None else gene_ids,
+            cell_filter_list=[], gene_filter_list=[], data_transf=_identity,
+            pp_data=None, remain_gene_inds=None, remain_cell_inds=None,
+            cluster_labels=np.zeros((n_cells, 1)))
 
     def set_data_transformation(self, data_transf):
         self.data_transf = data_transf
