@@ -28,9 +28,18 @@ import numpy as np  # noqa: E402
 GENES, CELLS, K = 20000, 100000, 8
 L1, L2 = 7.5, 2.5                      # alpha=10, l1_ratio=.75 (cmd_source.py:34-35)
 METRIC = "NMF MU iters/s (20k genes x 100k cells, k=8)"
-# dram__bytes_read.sum + dram__bytes_write.sum per sweep launch from the committed `ncu --set full` captures of
-# the default workload on one GPU (profiles/r01_sweep_full_raw.csv, profiles/r01_tcgen05_sweep_k8_full_raw.csv)
-NCU_TRAFFIC = {"simt": 8.003e9 + 0.03e9, "tcgen05": 8.018e9 + 0.014e9}
+
+
+def ncu_traffic(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum per sweep launch of the default workload on one GPU, as parsed
+    from this round's `ncu --set full` capture by tools/ncu_traffic.py into profiles/ncu_traffic.json
+    ({"f16" | "tcgen05" | "simt": {"bytes": ..., "source": ...}}); None when no capture of that kernel exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return float(json.load(f)[path]["bytes"])
+    except Exception:
+        return None
+
 UNIT = "iterations/s"
 E2E_ITERS = 100                        # NmfClustering.apply default max_iter (nmf_clustering.py:20)
 CPU_SAMPLE_CELLS = 10000
@@ -372,15 +381,20 @@ def run_gpu(args):
     peak, peak_src = measured_peaks()
     traffic = args.traffic
     if traffic is None and world == 1 and (genes, cells) == (GENES, CELLS):
-        traffic = NCU_TRAFFIC["tcgen05" if slv.tc else "simt"]
-    kname = ("wtx_tc_kernel<KP=%d> (tcgen05.mma kind::tf32%s)" % (slv.kp, ", TF32-exact X" if slv.tc_flags else "")
-             if slv.tc else "wtx_partial_kernel<KP=%d>" % slv.kp)
+        traffic = ncu_traffic("f16" if slv.half else ("tcgen05" if slv.tc else "simt"))
+    if slv.half:
+        kname = "wtx_h_kernel<KQ=%d> (tcgen05.mma kind::f16, fp16 storage of X and X^T)" % slv.kp
+    elif slv.tc:
+        kname = "wtx_tc_kernel<KP=%d> (tcgen05.mma kind::tf32%s)" % (slv.kp, ", TF32-exact X" if slv.tc_flags else "")
+    else:
+        kname = "wtx_partial_kernel<KP=%d>" % slv.kp
+    xbytes = 2 if slv.half else 4
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": kname, "peak_source": peak_src,
                 "launch_ms": avg_ms, "launches_timed": len(sweep_ms),
                 "sweep_share_of_step": sum(sweep_ms) / ms_eager,
                 "algorithmic_bytes_per_launch": sum(sweep_bytes) / len(sweep_bytes),
-                "iteration_algorithmic_gbs": (2 * genes * (c1 - c0) * 4 + 2 * (genes + (c1 - c0)) * k * 4)
+                "iteration_algorithmic_gbs": (2 * genes * (c1 - c0) * xbytes + 2 * (genes + (c1 - c0)) * k * 4)
                 / (ms / args.steps * 1e-3) / 1e9}
 
     # ---- end to end through the public API, from pinned host buffers -----------------------------
@@ -389,10 +403,11 @@ def run_gpu(args):
             emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                   "ms_per_step": ms / args.steps, "roofline": roofline, "gpu_launches": launches,
                   "note": "profiling run (--no-e2e): not a bench line"})
-        if world > 1:
-            dist.destroy_process_group()
+        slv.release()
+        shutdown_distributed(world)
         return
-    slv_tc, slv_kp = bool(slv.tc), slv.kp
+    slv_tc, slv_half, slv_kp, payload = bool(slv.tc), bool(slv.half), slv.kp, int(slv.R.numel())
+    slv.release()
     Xh = torch.empty((genes, n_loc), dtype=torch.float32).pin_memory()
     Xh.copy_(Xd[:, :n_loc])
     del slv, dm, Xd
@@ -451,12 +466,14 @@ def run_gpu(args):
             "config": {"workload": "NMF MU %d genes x %d cells k=%d, cells sharded over the GPUs "
                                    "(BASELINE.json configs[2])" % (genes, cells, k),
                        "genes": genes, "cells": cells, "k": k, "solver": "mu", "l1": L1, "l2": L2,
-                       "x_storage": "fp32 genes x cells + resident transposed copy",
-                       "sweep": "tcgen05 3xTF32 (kp=%d)" % slv_kp if slv_tc else "fp32 FMA (kp=%d)" % slv_kp,
+                       "x_storage": ("fp16 (every count exactly representable) genes x cells + resident transposed copy"
+                                     if slv_half else "fp32 genes x cells + resident transposed copy"),
+                       "sweep": ("tcgen05 kind::f16, 3-part fp16 factor split (kq=%d)" % slv_kp if slv_half else
+                                 "tcgen05 3xTF32 (kp=%d)" % slv_kp if slv_tc else "fp32 FMA (kp=%d)" % slv_kp),
                        "l2_flush": "none needed: each sweep streams %.1f GB per GPU, far larger than the 126 MB L2"
-                                   % (genes * n_loc * 4 / 1e9),
+                                   % (genes * n_loc * xbytes / 1e9),
                        "parallelism": "cells sharded x%d, one all-reduce of %d fp64 per iteration"
-                                      % (world, k * genes + k * k + 4) if world > 1 else "single GPU"},
+                                      % (world, payload) if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "frobenius_error_after_timed_steps": fro_after,
             "launch": {"mode": "cuda graph replay (one graph per iteration)" if (ms_graph is not None and ms == ms_graph)
@@ -465,8 +482,39 @@ def run_gpu(args):
             "cpu_baseline": cpu_baseline, "sc3_consensus": sc3,
         }
         emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown_distributed(world)
+
+
+def shutdown_distributed(world, limit_s=20.0):
+    """Tear the process group down and leave.  Round 1's 8-GPU arm printed its line and then never exited: a CUDA
+    graph that had captured NCCL all-reduces was still alive when the group was destroyed.  The solvers are
+    released by the caller; here: collect, synchronise, barrier, destroy -- all under a watchdog that ends the
+    process (exit code 0: the JSON line is already out) if NCCL's teardown stalls anyway."""
+    if world <= 1:
+        return
+    import gc
+    import threading
+    import torch
+    import torch.distributed as dist
+
+    def give_up():
+        sys.stderr.write("bench: process-group teardown exceeded %.0f s, leaving without it\n" % limit_s)
+        sys.stderr.flush()
+        os._exit(0)
+
+    dog = threading.Timer(limit_s, give_up)
+    dog.daemon = True
+    dog.start()
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+    if _OUT is not None:
+        _OUT.flush()
+    sys.stderr.flush()
+    # interpreter shutdown would run NCCL/CUDA destructors in arbitrary order: everything is flushed, leave now
+    os._exit(0)
 
 
 def _claim_stdout():

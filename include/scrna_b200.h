@@ -114,6 +114,38 @@ int scrna_tf32_inexact(const float* X, int64_t count, int32_t* inexact, void* st
 /* [hi | lo] TF32 operand shadow of a component-major fp64 master (kp x ld, element [t*ld + r]). */
 int scrna_nmf_tc_shadow(const double* F64, int64_t ld, int64_t rows, int k, int kp, float* Fs, void* stream);
 
+/* K1/K3 on 16-bit storage (tcgen05.mma kind::f16 fed straight from the TMA-staged tile): when every element
+ * of X is exactly representable in fp16 (raw counts <= 2048; scrna_f16_inexact reports 0) X and X^T are kept
+ * as fp16 (ldx multiple of 8 halves, 16-byte aligned base), halving the bytes of the HBM-bound iteration.
+ * Same contract and partial layout as scrna_nmf_wtx_partial with kp = kq = k rounded up to 8.  The factor is
+ * passed as its `parts`-part (2 or 3) fp16 operand shadow Fh (scrna_nmf_h_shadow_elems(g, kq, parts) halves,
+ * K-major MMA operand layout [(r/8)][n < NB][r%8], n = part*kq + t, NB = scrna_nmf_h_nb) of the factor scaled per
+ * component by a power of two; inv_scale[t] (kq floats) undoes the scale when the partial is stored.  Both are
+ * written by scrna_nmf_h_shadow / scrna_nmf_update.  x * part is exact in the fp32 accumulator; tensor memory
+ * is drained every 512 rows as in the TF32 sweep.  nsplit from scrna_nmf_wtx_h_splits.
+ * flags bits 8-23: drain period override in stages of 32 rows. */
+int scrna_nmf_h_supported(int kq);
+int scrna_nmf_h_nb(int kq, int parts);
+int64_t scrna_nmf_h_shadow_elems(int64_t rows, int kq, int parts);
+int scrna_nmf_wtx_h_splits(int g, int64_t ncols, int kq, int parts);
+int scrna_nmf_wtx_partial_h(const void* X16, int64_t ldx, int g, int64_t ncols, const void* Fh,
+                            const float* inv_scale, int kq, int parts, float* part, int64_t ldc, int nsplit,
+                            int flags, const scrna_nmf_ctrl_t* ctrl, void* stream);
+/* Three-part fp16 shadow of a component-major fp64 master (kp-stride Gram partials give the scale):
+ * scale_t = 2^e with ||F[:, t]|| * scale_t in [2^12, 2^13), ||.||^2 = sum over the `nblk` partial Grams
+ * gram_parts[p*kp*kp + t*kp + t] (nblk = 1: a finished kp x kp Gram).  gram_out != NULL additionally finishes
+ * the kp x kp Gram itself (fixed-order sum of the partials) in the same launch. */
+int scrna_nmf_h_shadow(const double* F64, int64_t ld, int64_t rows, int k, int kq, int parts,
+                       const double* gram_parts, int nblk, int kp, double* gram_out, void* Fh, float* inv_scale,
+                       const scrna_nmf_ctrl_t* ctrl, void* stream);
+/* inexact[0] = 1 if any of the `count` (multiple of 4) fp32 values is not exactly representable in fp16. */
+int scrna_f16_inexact(const float* X, int64_t count, int32_t* inexact, void* stream);
+/* fp32 -> fp16 storage: same layout (padding columns [cols, ld_dst) zeroed), and the transposed copy. */
+int scrna_narrow_f32_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst, int64_t ld_dst,
+                         void* stream);
+int scrna_transpose_f32_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst,
+                            int64_t ld_dst, void* stream);
+
 /* Sum the K1 partials over the splits in fixed order into fp64, component-major: out[t*ld + i]. */
 int scrna_nmf_reduce_rows(const float* part, int nsplit, int g, int kp, double* out, int64_t ld,
                           const scrna_nmf_ctrl_t* ctrl, void* stream);
@@ -140,6 +172,9 @@ int scrna_nmf_gram(const double* F, int64_t rs, int64_t cs, int64_t rows, int k,
  *   T32  : optional fp32 component-major shadow (kp x ld) read by scrna_residual / K1 variant 0;
  *   TC32 : optional [hi | lo] TF32 operand shadow read by scrna_nmf_wtx_partial_tc (rows and components
  *          beyond `rows` / `k` must have been zeroed once, e.g. by scrna_nmf_tc_shadow);
+ *   Fh, inv_scale, kq, parts : optional fp16 operand shadow + per-component unscale factors read by
+ *          scrna_nmf_wtx_partial_h (kq = k rounded up to 8); needs gram_partials -- the Gram finish and the
+ *          shadow share one launch (scrna_nmf_h_shadow);
  *   viol_part: scrna_nmf_update_blocks(rows) doubles, per-block sums of |projected gradient|.
  */
 int scrna_nmf_update_blocks(int64_t rows);
@@ -151,8 +186,8 @@ int scrna_nmf_update_blocks(int64_t rows);
 int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t rows, int k, int kp, const double* num,
                      const float* num_parts, int nsplit, const double* gram, double l1, double l2,
                      const int32_t* perms, int perm_stride, int perm_offset, float* S32, float* T32, float* TC32,
-                     double* viol_part, double* gram_partials, double* gram_out, scrna_nmf_ctrl_t* ctrl,
-                     void* stream);
+                     void* Fh, float* inv_scale, int kq, int parts, double* viol_part, double* gram_partials,
+                     double* gram_out, scrna_nmf_ctrl_t* ctrl, void* stream);
 /* Build the fp32 shadows of a component-major fp64 master (initial factors). */
 int scrna_nmf_shadows(const double* F64, int64_t ld, int64_t rows, int k, int kp, float* S32, float* T32,
                       void* stream);
@@ -182,6 +217,9 @@ int scrna_convert_pad_f64_f32(const double* src, int64_t ld_src, float* dst, int
 int scrna_residual_blocks(int64_t ncols, int kp);
 int scrna_residual(const float* X, int64_t ldx, int g, int64_t ncols, const float* G32, const float* C32,
                    int64_t ldc, int kp, int power, double* partials, double* out, void* stream);
+/* the same over fp16 storage of X (scrna_narrow_f32_f16) */
+int scrna_residual_h(const void* X16, int64_t ldx, int g, int64_t ncols, const float* G32, const float* C32,
+                     int64_t ldc, int kp, int power, double* partials, double* out, void* stream);
 
 /* out[0] = scale * sum(v[0..n)) in a fixed order (block partial sums -> one scalar; used for the
  * sharded part of the CD violation and for the error scalars before their all-reduce). */

@@ -25,7 +25,20 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("SCRNA_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference():
+    """The mounted reference tree, else the copy oracle/make_ref.py pip-installed into oracle/_ref/ (that one
+    travels to the GPU box; /root/reference does not)."""
+    env = os.environ.get("SCRNA_REFERENCE_ROOT")
+    for root in ([env] if env else []) + ["/root/reference", os.path.join(_HERE, "_ref")]:
+        if os.path.isdir(os.path.join(root, "scRNA")):
+            return root
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 _installed = False
 

@@ -1,5 +1,6 @@
 // Shared device/host helpers for libscrna_b200 (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -83,6 +84,33 @@ struct Vec<1> {
   __device__ __forceinline__ static Vec<1> cached(const float* p) { return Vec<1>{{__ldg(p)}}; }
   __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
 };
+
+// C consecutive elements of a row of X (fp32 or fp16 storage) as fp32, streaming
+template <int C>
+__device__ __forceinline__ Vec<C> load_x(const float* p) { return Vec<C>::stream(p); }
+template <int C>
+__device__ __forceinline__ Vec<C> load_x(const __half* p);
+template <>
+__device__ __forceinline__ Vec<4> load_x<4>(const __half* p) {
+  uint32_t a, b;
+  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&a));
+  const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&b));
+  return Vec<4>{{lo.x, lo.y, hi.x, hi.y}};
+}
+template <>
+__device__ __forceinline__ Vec<2> load_x<2>(const __half* p) {
+  uint32_t a;
+  asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(a) : "l"(p));
+  const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&a));
+  return Vec<2>{{v.x, v.y}};
+}
+template <>
+__device__ __forceinline__ Vec<1> load_x<1>(const __half* p) {
+  uint16_t a;
+  asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(a) : "l"(p));
+  return Vec<1>{{__half2float(__ushort_as_half(a))}};
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -516,7 +516,7 @@ static int grid_for(int64_t count, int threads) {
 
 using namespace scrna;
 
-extern "C" int scrna_abi_version(void) { return 1; }
+extern "C" int scrna_abi_version(void) { return 2; }
 
 extern "C" int scrna_device_info(int* sm_count, int* max_smem_per_block, int* cc_major, int* cc_minor) {
   int dev = 0;
@@ -576,10 +576,11 @@ extern "C" int scrna_nmf_update_blocks(int64_t rows) {
 extern "C" int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t rows, int k, int kp,
                                 const double* num, const float* num_parts, int nsplit, const double* gram,
                                 double l1, double l2, const int32_t* perms, int perm_stride, int perm_offset,
-                                float* S32, float* T32, float* TC32, double* viol_part, double* gram_partials,
-                                double* gram_out, scrna_nmf_ctrl_t* ctrl, void* stream) {
+                                float* S32, float* T32, float* TC32, void* Fh, float* inv_scale, int kq, int parts,
+                                double* viol_part, double* gram_partials, double* gram_out, scrna_nmf_ctrl_t* ctrl,
+                                void* stream) {
   if (!F64 || (!num && !num_parts) || (num_parts && nsplit <= 0) || !gram || rows <= 0 || ld < rows || k <= 0 ||
-      k > kp || kp > SCRNA_MAX_K || (kp & 3) || (gram_out && !gram_partials))
+      k > kp || kp > SCRNA_MAX_K || (kp & 3) || (gram_out && !gram_partials) || (Fh && (!gram_partials || !inv_scale)))
     return SCRNA_ERR_BADARG;
   const size_t smem = ((size_t)kp * kp + 2 * (size_t)k * UPD_LD) * sizeof(double);
   int nblk = (int)ceil_div(rows, UPD_THREADS);
@@ -609,6 +610,13 @@ extern "C" int scrna_nmf_update(int solver, double* F64, int64_t ld, int64_t row
                                                                   TC32, viol_part, gram_partials, (NmfCtrl*)ctrl);
   else
     return SCRNA_ERR_BADARG;
+  if (Fh) {
+    // fp16 operand shadow of the 16-bit sweep: needs the per-component scale, i.e. the Gram diagonal of the rows
+    // just written -- the Gram finish is folded into the same launch (nmf_sweep_h.cu)
+    if (int rc = last_launch_status()) return rc;
+    return scrna_nmf_h_shadow(F64, ld, rows, k, kq, parts, gram_partials, nblk, kp, gram_out, Fh, inv_scale, ctrl,
+                              stream);
+  }
   if (gram_out) {
     const int warps = kp * kp;
     gram_final_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(gram_partials, nblk, k, kp, gram_out,

@@ -41,9 +41,9 @@ transfer_mu_step_kernel(double* __restrict__ H64, float* __restrict__ H32, const
 // ---- K7 ---------------------------------------------------------------------------------------
 // Same streaming structure as K3: each lane owns C cells, keeps their KP x C factor entries in
 // registers, and the gene-factor rows are broadcast from shared memory.
-template <int KP, int C, int POWER>
+template <typename XT, int KP, int C, int POWER>
 __global__ void __launch_bounds__(256, 2)
-residual_kernel(const float* __restrict__ X, int64_t ldx, int g, int64_t ncols,
+residual_kernel(const XT* __restrict__ X, int64_t ldx, int g, int64_t ncols,
                 const float* __restrict__ G32, const float* __restrict__ C32, int64_t ldc,
                 int rows_per_split, int tile_rows, double* __restrict__ partials) {
   extern __shared__ float4 smem4[];
@@ -81,13 +81,13 @@ residual_kernel(const float* __restrict__ X, int64_t ldx, int g, int64_t ncols,
     }
     __syncthreads();
     if (!active) continue;
-    const float* xr = X + (int64_t)t0 * ldx + j0;
+    const XT* xr = X + (int64_t)t0 * ldx + j0;
     float part = 0.f;  // fp32 within a tile (<= a few thousand terms), fp64 across tiles
     for (int r = 0; r < nr; r += U) {
       Vec<C> xa[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (r + u < nr) xa[u] = Vec<C>::stream(xr + (int64_t)(r + u) * ldx);
+        if (r + u < nr) xa[u] = load_x<C>(xr + (int64_t)(r + u) * ldx);
         else
 #pragma unroll
           for (int c = 0; c < C; ++c) xa[u].v[c] = 0.f;
@@ -237,8 +237,8 @@ struct ResCfg {
   static constexpr int C = KP <= 8 ? 4 : (KP <= 16 ? 2 : 1);
 };
 
-template <int KP>
-static int residual_launch(const float* X, int64_t ldx, int g, int64_t ncols, const float* G32,
+template <typename XT, int KP>
+static int residual_launch(const XT* X, int64_t ldx, int g, int64_t ncols, const float* G32,
                            const float* C32, int64_t ldc, int power, double* partials, double* out,
                            int nsplit, cudaStream_t st) {
   constexpr int C = ResCfg<KP>::C;
@@ -250,9 +250,9 @@ static int residual_launch(const float* X, int64_t ldx, int g, int64_t ncols, co
   dim3 grid((unsigned)ceil_div(ncols, 8 * 32 * C), (unsigned)nsplit);
   const size_t smem = (size_t)tr * KP * sizeof(float);
   if (power == 1)
-    residual_kernel<KP, C, 1><<<grid, 256, smem, st>>>(X, ldx, g, ncols, G32, C32, ldc, rps, tr, partials);
+    residual_kernel<XT, KP, C, 1><<<grid, 256, smem, st>>>(X, ldx, g, ncols, G32, C32, ldc, rps, tr, partials);
   else
-    residual_kernel<KP, C, 2><<<grid, 256, smem, st>>>(X, ldx, g, ncols, G32, C32, ldc, rps, tr, partials);
+    residual_kernel<XT, KP, C, 2><<<grid, 256, smem, st>>>(X, ldx, g, ncols, G32, C32, ldc, rps, tr, partials);
   sum_partials_kernel<<<1, 256, 0, st>>>(partials, (int)(grid.x * grid.y), out, 1.0);
   return last_launch_status();
 }
@@ -269,20 +269,20 @@ static int residual_splits(int g, int64_t tiles) {
 
 using namespace scrna;
 
-#define SCRNA_DISPATCH_KP_T(kp, CALL)   \
+#define SCRNA_DISPATCH_KP_T(kp, ...)    \
   switch (kp) {                       \
-    case 4: { constexpr int KP = 4; CALL; } break;    \
-    case 8: { constexpr int KP = 8; CALL; } break;    \
-    case 12: { constexpr int KP = 12; CALL; } break;  \
-    case 16: { constexpr int KP = 16; CALL; } break;  \
-    case 20: { constexpr int KP = 20; CALL; } break;  \
-    case 24: { constexpr int KP = 24; CALL; } break;  \
-    case 28: { constexpr int KP = 28; CALL; } break;  \
-    case 32: { constexpr int KP = 32; CALL; } break;  \
-    case 40: { constexpr int KP = 40; CALL; } break;  \
-    case 48: { constexpr int KP = 48; CALL; } break;  \
-    case 56: { constexpr int KP = 56; CALL; } break;  \
-    case 64: { constexpr int KP = 64; CALL; } break;  \
+    case 4: { constexpr int KP = 4; __VA_ARGS__; } break;    \
+    case 8: { constexpr int KP = 8; __VA_ARGS__; } break;    \
+    case 12: { constexpr int KP = 12; __VA_ARGS__; } break;  \
+    case 16: { constexpr int KP = 16; __VA_ARGS__; } break;  \
+    case 20: { constexpr int KP = 20; __VA_ARGS__; } break;  \
+    case 24: { constexpr int KP = 24; __VA_ARGS__; } break;  \
+    case 28: { constexpr int KP = 28; __VA_ARGS__; } break;  \
+    case 32: { constexpr int KP = 32; __VA_ARGS__; } break;  \
+    case 40: { constexpr int KP = 40; __VA_ARGS__; } break;  \
+    case 48: { constexpr int KP = 48; __VA_ARGS__; } break;  \
+    case 56: { constexpr int KP = 56; __VA_ARGS__; } break;  \
+    case 64: { constexpr int KP = 64; __VA_ARGS__; } break;  \
     default: return SCRNA_ERR_UNSUPPORTED;            \
   }
 
@@ -301,8 +301,23 @@ extern "C" int scrna_residual(const float* X, int64_t ldx, int g, int64_t ncols,
   cudaStream_t st = (cudaStream_t)stream;
   SCRNA_DISPATCH_KP_T(kp, {
     const int64_t tiles = ceil_div(ncols, 8 * 32 * ResCfg<KP>::C);
-    return residual_launch<KP>(X, ldx, g, ncols, G32, C32, ldc, power, partials, out,
-                               residual_splits(g, tiles), st);
+    return residual_launch<float, KP>(X, ldx, g, ncols, G32, C32, ldc, power, partials, out,
+                                      residual_splits(g, tiles), st);
+  });
+  return SCRNA_ERR_UNSUPPORTED;
+}
+
+extern "C" int scrna_residual_h(const void* X16, int64_t ldx, int g, int64_t ncols, const float* G32,
+                                const float* C32, int64_t ldc, int kp, int power, double* partials,
+                                double* out, void* stream) {
+  if (!X16 || !G32 || !C32 || !partials || !out || g <= 0 || ncols <= 0 || (ldx & 3) || (ldc & 3) ||
+      (ncols & 3) || ncols > ldx || ncols > ldc || (power != 1 && power != 2))
+    return SCRNA_ERR_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  SCRNA_DISPATCH_KP_T(kp, {
+    const int64_t tiles = ceil_div(ncols, 8 * 32 * ResCfg<KP>::C);
+    return residual_launch<__half, KP>(reinterpret_cast<const __half*>(X16), ldx, g, ncols, G32, C32, ldc, power,
+                                       partials, out, residual_splits(g, tiles), st);
   });
   return SCRNA_ERR_UNSUPPORTED;
 }

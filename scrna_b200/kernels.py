@@ -4,6 +4,8 @@
 small method set so that the host-side logic (sharding, all-reduce packing, stop rules) can be
 exercised in tests with a stand-in provider; the product never constructs anything else.
 """
+import os
+
 from . import _lib
 
 
@@ -15,6 +17,7 @@ class CudaKernels:
         _lib.load()
         self.launches = 0  # number of kernels launched through the C ABI (bench.py: gpu_launches)
         self.sweep_events = None  # bench.py sets a list: (start, stop, X bytes) CUDA events per sweep launch
+        self.h_flags = int(os.environ.get("SCRNA_B200_H_FLAGS", "0"))  # bring-up probes of the 16-bit sweep
 
     def _s(self):
         return self.torch.cuda.current_stream().cuda_stream
@@ -74,6 +77,47 @@ class CudaKernels:
             b.record()
             ev.append((a, b, int(g) * int(ncols) * 4))
 
+    # ---- 16-bit storage path (nmf_sweep_h.cu) ---------------------------------------------------
+    def h_supported(self, kq):
+        return bool(_lib.call("scrna_nmf_h_supported", kq))
+
+    def h_nb(self, kq, parts):
+        return _lib.call("scrna_nmf_h_nb", kq, parts)
+
+    def h_shadow_elems(self, rows, kq, parts):
+        return _lib.call("scrna_nmf_h_shadow_elems", rows, kq, parts)
+
+    def wtx_h_splits(self, g, ncols, kq, parts):
+        return _lib.call("scrna_nmf_wtx_h_splits", g, ncols, kq, parts)
+
+    def wtx_partial_h(self, X16, ldx, g, ncols, Fh, inv_scale, kq, parts, part, ldc, nsplit, ctrl, flags=0):
+        ev = self.sweep_events
+        if ev is not None:
+            a = self.torch.cuda.Event(enable_timing=True)
+            b = self.torch.cuda.Event(enable_timing=True)
+            a.record()
+        self._call("scrna_nmf_wtx_partial_h", X16, ldx, g, ncols, Fh, inv_scale, kq, parts, part, ldc, nsplit,
+                   flags | self.h_flags, ctrl, self._s())
+        if ev is not None:
+            b.record()
+            ev.append((a, b, int(g) * int(ncols) * 2))
+
+    def h_shadow(self, F64, ld, rows, k, kq, parts, gram_parts, nblk, kp, gram_out, Fh, inv_scale, ctrl=None):
+        self._call("scrna_nmf_h_shadow", F64, ld, rows, k, kq, parts, gram_parts, nblk, kp, gram_out, Fh, inv_scale,
+                   ctrl, self._s())
+
+    def f16_exact(self, X):
+        """True if every element of the fp32 tensor is exactly representable in fp16."""
+        flag = self.torch.zeros(1, dtype=self.torch.int32, device=X.device)
+        self._call("scrna_f16_inexact", X, X.numel(), flag, self._s())
+        return int(flag.item()) == 0
+
+    def narrow_f16(self, src, ld_src, rows, cols, dst, ld_dst):
+        self._call("scrna_narrow_f32_f16", src, ld_src, rows, cols, dst, ld_dst, self._s())
+
+    def transpose_f16(self, src, ld_src, rows, cols, dst, ld_dst):
+        self._call("scrna_transpose_f32_f16", src, ld_src, rows, cols, dst, ld_dst, self._s())
+
     def tf32_exact(self, X):
         """True if every element of the fp32 tensor is exactly representable in TF32."""
         flag = self.torch.zeros(1, dtype=self.torch.int32, device=X.device)
@@ -94,12 +138,13 @@ class CudaKernels:
         self._call("scrna_nmf_gram", F64, rs, cs, rows, k, kp, partials, out, ctrl, self._s())
 
     def update(self, solver, F64, ld, rows, k, kp, num, gram, l1, l2, perms, perm_stride, perm_offset, S32, T32,
-               viol_part, ctrl, num_parts=None, nsplit=0, gram_partials=None, gram_out=None, TC32=None):
-        if gram_out is not None:
+               viol_part, ctrl, num_parts=None, nsplit=0, gram_partials=None, gram_out=None, TC32=None, Fh=None,
+               inv_scale=None, kq=0, parts=3):
+        if gram_out is not None or Fh is not None:
             self.launches += 1
         self._call("scrna_nmf_update", solver, F64, ld, rows, k, kp, num, num_parts, nsplit, gram, float(l1),
-                   float(l2), perms, perm_stride, perm_offset, S32, T32, TC32, viol_part, gram_partials, gram_out, ctrl,
-                   self._s())
+                   float(l2), perms, perm_stride, perm_offset, S32, T32, TC32, Fh, inv_scale, int(kq), int(parts), viol_part,
+                   gram_partials, gram_out, ctrl, self._s())
 
     def shadows(self, F64, ld, rows, k, kp, S32, T32):
         self._call("scrna_nmf_shadows", F64, ld, rows, k, kp, S32, T32, self._s())
@@ -121,7 +166,8 @@ class CudaKernels:
 
     def residual(self, X, ldx, g, ncols, G32, C32, ldc, kp, power, partials, out):
         self.launches += 1
-        self._call("scrna_residual", X, ldx, g, ncols, G32, C32, ldc, kp, power, partials, out, self._s())
+        name = "scrna_residual_h" if X.dtype == self.torch.float16 else "scrna_residual"
+        self._call(name, X, ldx, g, ncols, G32, C32, ldc, kp, power, partials, out, self._s())
 
     def sum_f64(self, v, n, out, scale=1.0):
         self._call("scrna_sum_f64", v, n, out, float(scale), self._s())

@@ -28,6 +28,9 @@ import numpy as np
 from . import _lib
 
 
+H_PARTS = 3   # fp16 parts of the factor in the 16-bit sweep (3: 33 significant bits; 2: 22, as the 3xTF32 sweep)
+
+
 def round_up(a, m):
     return ((int(a) + m - 1) // m) * m
 
@@ -57,8 +60,10 @@ class DeviceMatrix:
     """X shard: genes x cells, row-major fp32 on the device, leading dimension padded to 32 cells
     (128 B) and zero-filled beyond the real cells."""
 
-    def __init__(self, data, n, tf32_exact=None):
+    def __init__(self, data, n, tf32_exact=None, f16_exact=None):
         self.tf32_exact = tf32_exact   # every element representable in TF32 (raw counts < 2048): lazily probed
+        self.f16_exact = f16_exact     # every element representable in fp16 (raw counts <= 2048): lazily probed
+        self._half = None              # fp16 twin of an fp32 matrix (16-bit storage path), built once
         self.data = data
         self.g = int(data.shape[0])
         self.ldx = int(data.shape[1])
@@ -93,19 +98,43 @@ class DeviceMatrix:
             torch.cuda.current_stream().synchronize()
         return cls(out, n)
 
-    def transposed(self, kernels):
-        """Resident transposed copy: cells x genes fp32, leading dimension padded to 32 genes."""
+    @property
+    def is_half(self):
+        return self.data.element_size() == 2
+
+    def transposed(self, kernels, half=False):
+        """Resident transposed copy: cells x genes, leading dimension padded to 32 genes; fp32, or fp16 for the
+        16-bit storage path (always built from the fp32 matrix)."""
         torch = kernels.torch
         ldg = round_up(self.g, 32)
-        out = torch.zeros((max(self.n, 1), ldg), dtype=torch.float32, device=self.data.device)
+        if self.is_half:
+            raise ValueError("the transposed copy is built from the fp32 matrix")
+        out = torch.zeros((max(self.n, 1), ldg), dtype=torch.float16 if half else torch.float32,
+                          device=self.data.device)
         if self.n > 0:
-            kernels.transpose(self.data, self.ldx, self.g, self.n, out, ldg)
-        return DeviceMatrix(out, self.g, self.tf32_exact)
+            (kernels.transpose_f16 if half else kernels.transpose)(self.data, self.ldx, self.g, self.n, out, ldg)
+        return DeviceMatrix(out, self.g, self.tf32_exact, self.f16_exact)
+
+    def half_twin(self, kernels):
+        """fp16 storage of an fp16-exact fp32 matrix (same shape and leading dimension), built once and kept."""
+        if self.is_half:
+            return self
+        if self._half is None:
+            torch = kernels.torch
+            out = torch.empty((self.g, self.ldx), dtype=torch.float16, device=self.data.device)
+            kernels.narrow_f16(self.data, self.ldx, self.g, self.n, out, self.ldx)
+            self._half = DeviceMatrix(out, self.n, True, True)
+        return self._half
 
     def is_tf32_exact(self, kernels):
         if self.tf32_exact is None:
             self.tf32_exact = bool(kernels.tf32_exact(self.data))
         return self.tf32_exact
+
+    def is_f16_exact(self, kernels):
+        if self.f16_exact is None:
+            self.f16_exact = bool(kernels.f16_exact(self.data))
+        return self.f16_exact
 
 
 class TorchDistComm:
@@ -148,8 +177,10 @@ class NmfSolver:
     memory, and the component-major fp32 shadow Ct32 for the residual kernel."""
 
     def __init__(self, X, k, kernels=None, comm=None, transpose_copy=True, tensor_cores="auto", XT=None):
-        """tensor_cores: 'auto' = the tcgen05 sweep for k > 8 (where the FP32 pipe falls behind HBM) and, when
-        X is TF32-exact (raw counts), also for k <= 8; True / False force the choice."""
+        """tensor_cores: 'auto' = the 16-bit sweep (tcgen05 kind::f16 on fp16 storage of X and X^T) when every
+        element of X is exactly representable in fp16 (raw counts); else the 3xTF32 tcgen05 sweep for k > 8
+        (where the FP32 pipe falls behind HBM) and, when X is TF32-exact, also for k <= 8; else the FP32-pipe
+        sweep.  True = as 'auto' but never the FP32 pipe; 'f16' / 'tf32' / False force one path."""
         if kernels is None:
             from .kernels import default_kernels
             kernels = default_kernels()
@@ -157,25 +188,36 @@ class NmfSolver:
         self.torch = kernels.torch
         self.X = X
         self.k = int(k)
-        env = os.environ.get("SCRNA_B200_TC", "")   # "0" / "1" override the automatic choice (tests, A/B timing)
-        if env in ("0", "1") and tensor_cores == "auto":
-            tensor_cores = env == "1"
-        can_tc = bool(transpose_copy) and getattr(kernels, "tc_supported", lambda kp: False)(pad_k(self.k, True))
-        exact = False
-        if can_tc and tensor_cores:
-            # the shards must agree on the padded rank (it sizes the all-reduce payload): exact only if all are
-            inexact = kernels.torch.tensor([0.0 if X.is_tf32_exact(kernels) else 1.0], dtype=kernels.torch.float64,
-                                           device=X.data.device)
-            if comm is not None and comm.world > 1:
-                comm.all_reduce(inexact)
-            exact = float(inexact.item()) == 0.0
+        # SCRNA_B200_TC overrides the automatic choice (tests, A/B timing): "0" FP32 pipe, "1" / "tf32" the 3xTF32
+        # sweep, "f16" the 16-bit sweep wherever X allows it (else 3xTF32)
+        env = os.environ.get("SCRNA_B200_TC", "")
+        if env and tensor_cores == "auto":
+            tensor_cores = {"0": False, "1": "tf32", "tf32": "tf32", "f16": True}.get(env, "auto")
+        if tensor_cores not in ("auto", True, False, "f16", "tf32"):
+            raise ValueError("tensor_cores must be 'auto', True, False, 'f16' or 'tf32'")
+        self.comm = comm if (comm is not None and comm.world > 1) else None
+
+        def everywhere(flag):
+            # the shards must agree on the path (it sizes the all-reduce payload)
+            bad = kernels.torch.tensor([0.0 if flag else 1.0], dtype=kernels.torch.float64, device=X.data.device)
+            if self.comm is not None:
+                self.comm.all_reduce(bad)
+            return float(bad.item()) == 0.0
+
+        can_h = (bool(transpose_copy) and tensor_cores in ("auto", True, "f16")
+                 and getattr(kernels, "h_supported", lambda kq: False)(round_up(self.k, 8)))
+        self.half = can_h and everywhere(X.is_half or X.is_f16_exact(kernels))
+        if tensor_cores == "f16" and not self.half:
+            raise ValueError("tensor_cores='f16' needs the transposed copy and an fp16-exact X")
+        can_tc = (not self.half and bool(transpose_copy) and tensor_cores in ("auto", True, "tf32")
+                  and getattr(kernels, "tc_supported", lambda kp: False)(pad_k(self.k, True)))
+        exact = can_tc and everywhere(X.is_tf32_exact(kernels))
         if tensor_cores == "auto":
             self.tc = can_tc and (self.k > 8 or exact)
         else:
-            self.tc = bool(tensor_cores) and can_tc
-        self.kp = pad_k(self.k, self.tc)
+            self.tc = can_tc
+        self.kp = round_up(self.k, 8) if self.half else pad_k(self.k, self.tc)
         self.tc_flags = 32 if (self.tc and exact) else 0
-        self.comm = comm if (comm is not None and comm.world > 1) else None
         t = self.torch
         dev = X.data.device
         g, n, kp = X.g, max(X.n, 1), self.kp
@@ -183,28 +225,37 @@ class NmfSolver:
         self.ldg = ldg = round_up(g, 32)
         self.gcols = round_up(g, 4)
         f64, f32 = t.float64, t.float32
-        if XT is not None and transpose_copy:
+        self.Xs = X.half_twin(kernels) if self.half else X     # the matrix the sweeps stream
+        if XT is not None and transpose_copy and XT.is_half == self.half:
             self.XT = XT          # a resident transposed copy built by another solver on the same X
         else:
-            self.XT = X.transposed(kernels) if transpose_copy else None
+            self.XT = X.transposed(kernels, half=self.half) if transpose_copy else None
         self.G64 = t.zeros((kp, ldg), dtype=f64, device=dev)
         self.Gs32 = t.zeros((g, kp), dtype=f32, device=dev)
         self.C64 = t.zeros((kp, ldn), dtype=f64, device=dev)
         self.Cs32 = t.zeros((n, kp), dtype=f32, device=dev)
         self.Ct32 = t.zeros((kp, ldn), dtype=f32, device=dev)
-        if self.tc:
+        self.Gtc = self.Ctc = self.Gh = self.Ch = self.Ginv = self.Cinv = None
+        self.h_parts = hp = int(os.environ.get("SCRNA_B200_H_PARTS", H_PARTS))
+        if self.half:
+            self.Gh = t.zeros(kernels.h_shadow_elems(g, kp, hp), dtype=t.float16, device=dev)
+            self.Ch = t.zeros(kernels.h_shadow_elems(n, kp, hp), dtype=t.float16, device=dev)
+            self.Ginv = t.ones(kp, dtype=f32, device=dev)
+            self.Cinv = t.ones(kp, dtype=f32, device=dev)
+            self.SA = int(os.environ.get("SCRNA_B200_TC_SA", 0)) or kernels.wtx_h_splits(n, self.gcols, kp, hp)
+            self.PA = t.zeros((self.SA, kp, ldg), dtype=f32, device=dev)
+            self.SB = int(os.environ.get("SCRNA_B200_TC_SB", 0)) or kernels.wtx_h_splits(g, X.ncols, kp, hp)
+        elif self.tc:
             self.Gtc = t.zeros(kernels.tc_shadow_elems(g, kp), dtype=f32, device=dev)
             self.Ctc = t.zeros(kernels.tc_shadow_elems(n, kp), dtype=f32, device=dev)
             self.SA = int(os.environ.get("SCRNA_B200_TC_SA", 0)) or kernels.wtx_tc_splits(n, self.gcols, kp)
             self.PA = t.zeros((self.SA, kp, ldg), dtype=f32, device=dev)
             self.SB = int(os.environ.get("SCRNA_B200_TC_SB", 0)) or kernels.wtx_tc_splits(g, X.ncols, kp)
         elif self.XT is not None:
-            self.Gtc = self.Ctc = None
             self.SA = kernels.wtx_splits(n, self.gcols, kp)
             self.PA = t.zeros((self.SA, kp, ldg), dtype=f32, device=dev)
             self.SB = kernels.wtx_splits(g, X.ncols, kp)
         else:
-            self.Gtc = self.Ctc = None
             self.SA = kernels.xht_splits(g, X.ncols, kp)
             self.PA = t.zeros((self.SA, g, kp), dtype=f32, device=dev)
             self.SB = kernels.wtx_splits(g, X.ncols, kp)
@@ -243,6 +294,9 @@ class NmfSolver:
         self.kn.shadows(self.G64, self.ldg, X.g, k, kp, self.Gs32, None)
         if self.tc:
             self.kn.tc_shadow(self.G64, self.ldg, X.g, k, kp, self.Gtc)
+        if self.half:   # the fp16 parts are scaled by the column norm: Gram first
+            self._gram_G(None)
+            self.kn.h_shadow(self.G64, self.ldg, X.g, k, kp, self.h_parts, self.gtg, 1, kp, None, self.Gh, self.Ginv)
 
     def load_C(self, C0):
         """Cell factor (k x n host array) -> fp64 master + shadows."""
@@ -256,6 +310,10 @@ class NmfSolver:
         self.kn.shadows(self.C64, self.ldn, max(X.n, 1), k, kp, self.Cs32, self.Ct32)
         if self.tc:
             self.kn.tc_shadow(self.C64, self.ldn, max(X.n, 1), k, kp, self.Ctc)
+        if self.half:
+            self._gram_C(None)
+            self.kn.h_shadow(self.C64, self.ldn, max(X.n, 1), k, kp, self.h_parts, self.R_cct, 1, kp, None, self.Ch,
+                             self.Cinv)
 
     def _load_factors(self, G0, C0):
         self.load_G(G0)
@@ -276,18 +334,14 @@ class NmfSolver:
         """X^T @ Q for a host (g x k) matrix Q: one sweep of X.  Returns this shard's n x k fp64."""
         kn, X, kp = self.kn, self.X, self.kp
         self.load_G(Q)
-        if self.tc:
-            kn.wtx_partial_tc(X.data, X.ldx, X.g, X.ncols, self.Gtc, kp, self.PB, self.ldn, self.SB, None,
-                              flags=self.tc_flags)
-        else:
-            kn.wtx_partial(X.data, X.ldx, X.g, X.ncols, self.Gs32, kp, self.PB, self.ldn, self.SB, None)
+        self._sweep_X(None)
         kn.reduce_cols(self.PB, self.SB, kp, self.ldn, X.ncols, self.NB, None)
         return np.ascontiguousarray(self.NB[: self.k, : X.n].cpu().numpy().T)
 
     def x_sum(self):
         """sum_ij |X_ij| over this shard (= sum X for the non-negative NMF input): the residual kernel
         against all-zero factors."""
-        X = self.X
+        X = self.Xs
         self.Gs32.zero_()
         self.Ct32.zero_()
         self.kn.residual(X.data, X.ldx, X.g, X.ncols, self.Gs32, self.Ct32, self.ldn, self.kp, 1, self.res_part,
@@ -309,6 +363,31 @@ class NmfSolver:
         C = self.C64[:k, : X.n].cpu().numpy().copy()
         return G, C
 
+    # ---- the two sweeps -----------------------------------------------------------------------
+    def _sweep_X(self, ctrl):
+        """K3: G^T . X over this shard -> split partials PB (SB x kp x ldn)."""
+        kn, X, kp = self.kn, self.Xs, self.kp
+        if self.half:
+            kn.wtx_partial_h(X.data, X.ldx, X.g, X.ncols, self.Gh, self.Ginv, kp, self.h_parts, self.PB, self.ldn,
+                             self.SB, ctrl)
+        elif self.tc:
+            kn.wtx_partial_tc(X.data, X.ldx, X.g, X.ncols, self.Gtc, kp, self.PB, self.ldn, self.SB, ctrl,
+                              flags=self.tc_flags)
+        else:
+            kn.wtx_partial(X.data, X.ldx, X.g, X.ncols, self.Gs32, kp, self.PB, self.ldn, self.SB, ctrl)
+
+    def _sweep_XT(self, ctrl):
+        """K1 on the transposed copy: (X . C^T)^T -> split partials PA (SA x kp x ldg)."""
+        kn, XT, kp = self.kn, self.XT, self.kp
+        if self.half:
+            kn.wtx_partial_h(XT.data, XT.ldx, XT.g, self.gcols, self.Ch, self.Cinv, kp, self.h_parts, self.PA, self.ldg,
+                             self.SA, ctrl)
+        elif self.tc:
+            kn.wtx_partial_tc(XT.data, XT.ldx, XT.g, self.gcols, self.Ctc, kp, self.PA, self.ldg, self.SA, ctrl,
+                              flags=self.tc_flags)
+        else:
+            kn.wtx_partial(XT.data, XT.ldx, XT.g, self.gcols, self.Cs32, kp, self.PA, self.ldg, self.SA, ctrl)
+
     # ---- the two half steps -------------------------------------------------------------------
     def _gram_C(self, ctrl):
         self.kn.gram(self.C64, 1, self.ldn, max(self.X.n, 1), self.k, self.kp, self.gram_part, self.R_cct, ctrl)
@@ -322,12 +401,7 @@ class NmfSolver:
         cell-factor epilogue (or by _gram_C for the initial / a fixed C)."""
         kn, X, kp = self.kn, self.X, self.kp
         if self.XT is not None:
-            XT = self.XT
-            if self.tc:
-                kn.wtx_partial_tc(XT.data, XT.ldx, XT.g, self.gcols, self.Ctc, kp, self.PA, self.ldg, self.SA, ctrl,
-                                  flags=self.tc_flags)
-            else:
-                kn.wtx_partial(XT.data, XT.ldx, XT.g, self.gcols, self.Cs32, kp, self.PA, self.ldg, self.SA, ctrl)
+            self._sweep_XT(ctrl)
             if self._g_num_from_R:
                 kn.reduce_cols(self.PA, self.SA, kp, self.ldg, self.gcols, self.R_xht, ctrl)
         else:
@@ -346,29 +420,27 @@ class NmfSolver:
                        None if fused else self.R_xht, self.R_cct, l1, l2, self.perms, stride, offset,
                        self.Gs32, None, self.violG, ctrl,
                        num_parts=self.PA if fused else None, nsplit=self.SA if fused else 0,
-                       gram_partials=self.gpartG, gram_out=self.gtg, TC32=self.Gtc)
+                       gram_partials=self.gpartG, gram_out=self.gtg, TC32=self.Gtc, Fh=self.Gh, inv_scale=self.Ginv,
+                       kq=self.kp, parts=self.h_parts)
 
     def _half_C(self, solver, l1, l2, stride, offset, ctrl):
         kn, X, kp = self.kn, self.X, self.kp
-        if self.tc:
-            kn.wtx_partial_tc(X.data, X.ldx, X.g, X.ncols, self.Gtc, kp, self.PB, self.ldn, self.SB, ctrl,
-                              flags=self.tc_flags)
-        else:
-            kn.wtx_partial(X.data, X.ldx, X.g, X.ncols, self.Gs32, kp, self.PB, self.ldn, self.SB, ctrl)
+        self._sweep_X(ctrl)
         if self.fuse_reduce:
             kn.update(solver, self.C64, self.ldn, max(X.n, 1), self.k, kp, None, self.gtg, l1, l2,
                       self.perms, stride, offset, self.Cs32, self.Ct32, self.violC, ctrl,
                       num_parts=self.PB, nsplit=self.SB, gram_partials=self.gpartC, gram_out=self.R_cct,
-                      TC32=self.Ctc)
+                      TC32=self.Ctc, Fh=self.Ch, inv_scale=self.Cinv, kq=kp, parts=self.h_parts)
         else:
             kn.reduce_cols(self.PB, self.SB, kp, self.ldn, X.ncols, self.NB, ctrl)
             kn.update(solver, self.C64, self.ldn, max(X.n, 1), self.k, kp, self.NB, self.gtg, l1, l2,
                       self.perms, stride, offset, self.Cs32, self.Ct32, self.violC, ctrl,
-                      gram_partials=self.gpartC, gram_out=self.R_cct, TC32=self.Ctc)
+                      gram_partials=self.gpartC, gram_out=self.R_cct, TC32=self.Ctc, Fh=self.Ch, inv_scale=self.Cinv,
+                      kq=kp, parts=self.h_parts)
 
     def frobenius_error(self):
         """||X - G.C||_F over all shards (sklearn _beta_divergence(..., square_root=True))."""
-        X = self.X
+        X = self.Xs
         self.kn.residual(X.data, X.ldx, X.g, X.ncols, self.Gs32, self.Ct32, self.ldn, self.kp, 2, self.res_part,
                          self.res_out)
         if self.comm is not None:
@@ -482,6 +554,14 @@ class NmfSolver:
         self._graph = g
         self.step = g.replay
         return g
+
+    def release(self):
+        """Drop the captured CUDA graph and the launch-sequence closures (`step` <-> `one_iteration` reference
+        this object, so `del solver` alone never frees a graph that captured NCCL work).  Call before
+        `torch.distributed.destroy_process_group()`."""
+        self._graph = None
+        self.step = None
+        self._one_iteration = None
 
     def fit(self, G0, C0, solver="cd", l1_G=0.0, l2_G=0.0, l1_C=0.0, l2_C=0.0, tol=1e-4, max_iter=200,
             update_G=True, update_C=True, first="G", seed=0, shuffle=True, perms=None, poll=4,

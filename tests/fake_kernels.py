@@ -30,6 +30,7 @@ class FakeKernels:
     def update_blocks(self, rows): return (rows + 127) // 128
     def residual_blocks(self, ncols, kp): return 8
     def tc_supported(self, kp): return False
+    def h_supported(self, kq): return False
 
     @staticmethod
     def _done(ctrl):
@@ -72,7 +73,8 @@ class FakeKernels:
         o[:k, :k] = F @ F.T
 
     def update(self, solver, F64, ld, rows, k, kp, num, gram, l1, l2, perms, perm_stride, perm_offset, S32, T32,
-               viol_part, ctrl, num_parts=None, nsplit=0, gram_partials=None, gram_out=None, TC32=None):
+               viol_part, ctrl, num_parts=None, nsplit=0, gram_partials=None, gram_out=None, TC32=None, Fh=None,
+               inv_scale=None, kq=0, parts=3):
         if self._done(ctrl): return
         F = _np(F64)
         W = np.ascontiguousarray(F[:k, :rows].T)

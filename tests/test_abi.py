@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 def test_python_binding_covers_header():
     assert sorted(_lib.exported_symbols()) == declared_symbols()
     lib = _lib.load()
-    assert lib.scrna_abi_version() == 1
+    assert lib.scrna_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

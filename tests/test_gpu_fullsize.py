@@ -26,13 +26,14 @@ def _factors(k, seed=0):
     return 0.3 * np.abs(rng.standard_normal((GENES, k))), 0.3 * np.abs(rng.standard_normal((k, CELLS)))
 
 
+@pytest.mark.parametrize("path", ["f16", "tf32"])
 @pytest.mark.parametrize("k", [8, 32])
-def test_full_size_sweeps_linear_consistent_deterministic(kernels, big, k):
+def test_full_size_sweeps_linear_consistent_deterministic(kernels, big, k, path):
     from scrna_b200.nmf_solver import NmfSolver
     torch = kernels.torch
-    tc = NmfSolver(big, k, kernels=kernels, tensor_cores=True)
+    tc = NmfSolver(big, k, kernels=kernels, tensor_cores=path)
     fp = NmfSolver(big, k, kernels=kernels, tensor_cores=False, XT=tc.XT)
-    assert tc.tc and not fp.tc
+    assert (tc.half if path == "f16" else tc.tc) and not fp.tc and not fp.half
     G1, _ = _factors(k, 1)
     G2, _ = _factors(k, 2)
     a = tc.xt_times(G1)

@@ -27,12 +27,108 @@ def _solver(kernels, X, k, transpose_copy=True, tensor_cores="auto"):
                      tensor_cores=tensor_cores)
 
 
-@pytest.fixture(params=["simt", "tcgen05"])
+@pytest.fixture(params=["simt", "tcgen05", "f16"])
 def sweep_path(request, monkeypatch):
-    """Runs a test once on the FP32-pipe sweeps and once on the tcgen05 sweep (SCRNA_B200_TC override of the
-    solver's automatic choice; the classes construct their solver internally)."""
-    monkeypatch.setenv("SCRNA_B200_TC", "1" if request.param == "tcgen05" else "0")
+    """Runs a test once on the FP32-pipe sweeps, once on the 3xTF32 tcgen05 sweep and once on the 16-bit-storage
+    tcgen05 sweep (SCRNA_B200_TC override of the solver's automatic choice; the classes construct their solver
+    internally; 'f16' falls back to 3xTF32 for matrices that are not fp16-exact, e.g. the mixed target data)."""
+    monkeypatch.setenv("SCRNA_B200_TC", {"simt": "0", "tcgen05": "tf32", "f16": "f16"}[request.param])
     return request.param
+
+
+@pytest.mark.parametrize("g,n,k", [(1000, 1000, 8), (333, 517, 7), (64, 4100, 5), (2500, 130, 16), (129, 257, 33),
+                                   (40, 36, 3), (700, 900, 50), (5, 7, 2), (3000, 2000, 64), (1037, 1500, 17),
+                                   (2100, 1300, 24), (900, 700, 40)])
+def test_f16_sweeps_match_fp64_products(kernels, g, n, k):
+    """The 16-bit sweep (fp16 storage of X and X^T staged by swizzled TMA boxes straight into tcgen05.mma kind::f16,
+    three-part scaled fp16 split of the factor) on both resident copies, against fp64 products; counts up to
+    fp16's exact-integer limit 2048 and factors with a wide dynamic range."""
+    torch = kernels.torch
+    rng = np.random.RandomState(g + 3 * n + k)
+    X = rng.poisson(2.0, size=(g, n)).astype(np.float64)
+    X[rng.rand(g, n) < 0.01] = 2048.0
+    X[rng.rand(g, n) < 0.01] = 1777.0
+    G = (np.abs(rng.randn(g, k)) + 0.01) * np.exp(3.0 * rng.randn(1, k))
+    C = (np.abs(rng.randn(k, n)) + 0.01) * np.exp(2.0 * rng.randn(k, n))
+    slv = _solver(kernels, X, k, tensor_cores="f16")
+    assert slv.half and not slv.tc and slv.kp % 8 == 0 and slv.Xs.is_half and slv.XT.is_half
+    np.testing.assert_array_equal(slv.Xs.data[:, :n].float().cpu().numpy(), X.astype(np.float32))
+    np.testing.assert_array_equal(slv.XT.data[:n, :g].float().cpu().numpy(), X.T.astype(np.float32))
+    assert float(slv.XT.data[:, g:].float().abs().sum().cpu()) == 0.0
+    slv._load_factors(G, C)
+    slv._g_num_from_R = True
+    slv._products_for_G(None, with_gram=True)
+    torch.cuda.synchronize()
+    xht = slv.R_xht.view(slv.kp, slv.ldg)[:k, :g].cpu().numpy().T
+    assert rel_fro(xht, X @ C.T) < 5e-6     # the tensor core truncates its fp32 accumulator (see nmf_sweep_tc.cu)
+    assert np.all(slv.R_xht.view(slv.kp, slv.ldg)[k:, :g].cpu().numpy() == 0)
+    slv._sweep_X(None)
+    kernels.reduce_cols(slv.PB, slv.SB, slv.kp, slv.ldn, slv.X.ncols, slv.NB, None)
+    torch.cuda.synchronize()
+    wtx = slv.NB[:k, :n].cpu().numpy()
+    ref = G.T @ X
+    assert rel_fro(wtx, ref) < 5e-6
+    assert np.all(slv.NB[k:, :n].cpu().numpy() == 0)
+    # elementwise and per component: no tile of the mapping is misplaced, no component loses accuracy to its scale
+    for t in range(k):
+        assert np.max(np.abs(wtx[t] - ref[t])) < 1e-5 * np.abs(ref[t]).max(), t
+    # residual over the fp16 storage
+    Gs, Cs = slv.Gs32.cpu().numpy().astype(np.float64)[:, :k], slv.Ct32.cpu().numpy().astype(np.float64)[:k, :n]
+    assert abs(slv.frobenius_error() - np.linalg.norm(X - Gs @ Cs)) / np.linalg.norm(X - Gs @ Cs) < 2e-5
+
+
+def test_f16_not_chosen_for_inexact_data(kernels):
+    rng = np.random.RandomState(0)
+    X = rng.poisson(2.0, size=(200, 300)).astype(np.float64)
+    assert _solver(kernels, X, 6).half
+    X[3, 4] = 2049.0                                      # not an fp16 value
+    assert not _solver(kernels, X, 6).half
+    X[3, 4] = 0.1
+    assert not _solver(kernels, X, 6).half
+    with pytest.raises(ValueError):
+        _solver(kernels, X, 6, tensor_cores="f16")
+
+
+def test_update_writes_f16_operand_shadow(kernels):
+    """The epilogue's three-part fp16 shadow equals the one scrna_nmf_h_shadow builds from the master and its Gram,
+    and the parts reconstruct the master to 2^-33 of the column norm."""
+    import scrna_b200._lib as L
+    torch = kernels.torch
+    rng = np.random.RandomState(5)
+    rows, k, kq, ld = 1001, 13, 16, 1024
+    dev = torch.device("cuda")
+    F = np.zeros((kq, ld)); F[:k, :rows] = np.abs(rng.randn(k, rows)) * np.exp(4.0 * rng.randn(k, 1))
+    F64 = torch.from_numpy(F).to(dev)
+    N = np.zeros((kq, ld)); N[:k, :rows] = np.abs(rng.randn(k, rows)) * 10
+    A = np.abs(rng.randn(40, k)); Gm = np.zeros((kq, kq)); Gm[:k, :k] = A.T @ A
+    n_el = kernels.h_shadow_elems(rows, kq, 3)
+    nb = kernels.h_nb(kq, 3)
+    sh_a = torch.zeros(n_el, dtype=torch.float16, device=dev)
+    sh_b = torch.full((n_el,), -1.0, dtype=torch.float16, device=dev)
+    inv_a = torch.zeros(kq, dtype=torch.float32, device=dev)
+    inv_b = torch.zeros(kq, dtype=torch.float32, device=dev)
+    S32 = torch.zeros((rows, kq), dtype=torch.float32, device=dev)
+    nblk = kernels.update_blocks(rows)
+    viol = torch.zeros(nblk, dtype=torch.float64, device=dev)
+    gpart = torch.zeros(nblk * kq * kq, dtype=torch.float64, device=dev)
+    gout = torch.zeros(kq * kq, dtype=torch.float64, device=dev)
+    ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
+    kernels.update(L.SOLVER_MU, F64, ld, rows, k, kq, torch.from_numpy(N).to(dev), torch.from_numpy(Gm).to(dev), 0.5, 0.1,
+                   None, 1, 0, S32, None, viol, ctrl, gram_partials=gpart, gram_out=gout, Fh=sh_a, inv_scale=inv_a, kq=kq, parts=3)
+    torch.cuda.synchronize()
+    got = F64.cpu().numpy()[:k, :rows]
+    np.testing.assert_allclose(gout.cpu().numpy().reshape(kq, kq)[:k, :k], got @ got.T, rtol=1e-12)
+    kernels.h_shadow(F64, ld, rows, k, kq, 3, gout, 1, kq, None, sh_b, inv_b)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(sh_a.cpu().numpy(), sh_b.cpu().numpy())
+    np.testing.assert_array_equal(inv_a.cpu().numpy(), inv_b.cpu().numpy())
+    sh = sh_b.cpu().numpy().astype(np.float64).reshape(-1, nb, 8)             # [(r/8)][n][r%8]
+    inv = inv_b.cpu().numpy().astype(np.float64)
+    assert np.all(np.isfinite(sh)) and np.abs(sh).max() <= 2.0 ** 13
+    parts = [sh[:, p * kq:(p + 1) * kq, :].transpose(1, 0, 2).reshape(kq, -1)[:k, :rows] for p in range(3)]
+    rec = (parts[0] + parts[1] + parts[2]) * inv[:k, None]
+    assert np.max(np.abs(rec - got) / np.linalg.norm(got, axis=1, keepdims=True)) < 2.0 ** -33
+    assert np.all(sh[:, 3 * kq:, :] == 0) and np.all(sh[:, :, :].reshape(-1, nb, 8)[:, k:kq, :] == 0)
 
 
 @pytest.mark.parametrize("exact_x", [True, False])
@@ -49,7 +145,7 @@ def test_tcgen05_sweeps_match_fp64_products(kernels, g, n, k, exact_x):
         X = rng.rand(g, n) * np.exp(2.0 * rng.randn(g, n))
     G = np.abs(rng.randn(g, k)) + 0.01
     C = np.abs(rng.randn(k, n)) + 0.01
-    slv = _solver(kernels, X, k, tensor_cores=True)
+    slv = _solver(kernels, X, k, tensor_cores="tf32")
     assert slv.tc and slv.kp % 16 == 0 and (slv.tc_flags == 32) == exact_x
     slv._load_factors(G, C)
     slv._g_num_from_R = True

@@ -38,7 +38,7 @@ def main():
     ap.add_argument("--sb", type=int, nargs="*", default=[])
     ap.add_argument("--lowmem", action="store_true")
     ap.add_argument("--variants", type=int, nargs="*", default=[2])
-    ap.add_argument("--tc", default="auto", help="auto | 0 | 1: tcgen05 sweep choice passed to NmfSolver")
+    ap.add_argument("--tc", default="auto", help="auto | 0 | 1 | f16 | tf32: sweep choice passed to NmfSolver")
     ap.add_argument("--real", action="store_true", help="non-integer X (general 3xTF32 path, Xl pass on)")
     ap.add_argument("--out", default="gpurun_out/kbench.json")
     args = ap.parse_args()
@@ -59,7 +59,7 @@ def main():
     bytes_x = g * ldx * 4
     out = []
     for k in args.k:
-        tc = {"auto": "auto", "0": False, "1": True}[args.tc]
+        tc = {"auto": "auto", "0": False, "1": True, "f16": "f16", "tf32": "tf32"}[args.tc]
         slv = NmfSolver(dm, k, kernels=kn, tensor_cores=tc)
         rng = np.random.RandomState(0)
         G0 = np.abs(rng.randn(g, k)); C0 = np.abs(rng.randn(k, n))
@@ -67,19 +67,21 @@ def main():
         kp = slv.kp
         sa_list = args.sa or [slv.SA]
         sb_list = args.sb or [slv.SB]
-        if slv.tc:
-            med, best = timeit(lambda: kn.wtx_partial_tc(X, ldx, g, dm.ncols, slv.Gtc, kp, slv.PB, slv.ldn, slv.SB, None,
-                                                         flags=slv.tc_flags))
-            out.append(dict(kernel="sweep_X(tcgen05)", k=k, kp=kp, exact=slv.tc_flags == 32, nsplit=slv.SB, ms=med,
-                            best_ms=best, gbs=bytes_x / med / 1e6))
+        if slv.tc or slv.half:
+            eb = 2 if slv.half else 4
+            name = "tcgen05 f16" if slv.half else "tcgen05 tf32"
+            med, best = timeit(lambda: slv._sweep_X(None))
+            out.append(dict(kernel="sweep_X(%s)" % name, k=k, kp=kp, exact=slv.half or slv.tc_flags == 32, nsplit=slv.SB,
+                            ms=med, best_ms=best, gbs=g * ldx * eb / med / 1e6))
             print(out[-1], flush=True)
             XT = slv.XT
-            med, best = timeit(lambda: kn.wtx_partial_tc(XT.data, XT.ldx, XT.g, slv.gcols, slv.Ctc, kp, slv.PA, slv.ldg,
-                                                         slv.SA, None, flags=slv.tc_flags))
-            out.append(dict(kernel="sweep_XT(tcgen05)", k=k, kp=kp, exact=slv.tc_flags == 32, nsplit=slv.SA, ms=med,
-                            best_ms=best, gbs=XT.g * XT.ldx * 4 / med / 1e6))
+            med, best = timeit(lambda: slv._sweep_XT(None))
+            out.append(dict(kernel="sweep_XT(%s)" % name, k=k, kp=kp, exact=slv.half or slv.tc_flags == 32, nsplit=slv.SA,
+                            ms=med, best_ms=best, gbs=XT.g * XT.ldx * eb / med / 1e6))
             print(out[-1], flush=True)
             sb_list, sa_list = [], []
+            if slv.half:
+                bytes_x = g * ldx * 2
         for sb in sb_list:
           for var in args.variants:
             PB = torch.zeros((sb, kp, slv.ldn), dtype=torch.float32, device=dev)
@@ -102,7 +104,8 @@ def main():
             med, best = timeit(lambda: kn.xht_partial(X, ldx, g, dm.ncols, slv.Ct32, slv.ldn, kp, PA0, sa0, None))
             out.append(dict(kernel="xht_partial(lowmem K1)", k=k, nsplit=sa0, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
             print(out[-1], flush=True)
-        med, best = timeit(lambda: kn.residual(X, ldx, g, dm.ncols, slv.Gs32, slv.Ct32, slv.ldn, kp, 1, slv.res_part, slv.res_out))
+        Xr = slv.Xs.data
+        med, best = timeit(lambda: kn.residual(Xr, ldx, g, dm.ncols, slv.Gs32, slv.Ct32, slv.ldn, kp, 1, slv.res_part, slv.res_out))
         out.append(dict(kernel="residual_l1", k=k, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
         print(out[-1], flush=True)
         # whole iterations
