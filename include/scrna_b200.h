@@ -116,22 +116,28 @@ int scrna_nmf_tc_shadow(const double* F64, int64_t ld, int64_t rows, int k, int 
 
 /* K1/K3 on 16-bit storage (tcgen05.mma kind::f16 fed straight from the TMA-staged tile): when every element
  * of X is exactly representable in fp16 (raw counts <= 2048; scrna_f16_inexact reports 0) X and X^T are kept
- * as fp16 (ldx multiple of 8 halves, 16-byte aligned base), halving the bytes of the HBM-bound iteration.
+ * as fp16, halving the bytes of the HBM-bound iteration.
+ * Storage is PANEL-MAJOR: panels of 256 columns, element (i, j) at ((j/256)*rows_pad + i)*256 + j%256 with
+ * rows_pad = scrna_f16_panel_rows(rows) (rows rounded up to 64) and all padding zero -- the rows a CTA streams
+ * are one contiguous region of HBM per panel; scrna_f16_panel_elems(rows, cols) halves, 128-byte aligned base;
+ * written by scrna_narrow_f32_f16 / scrna_transpose_f32_f16.
  * Same contract and partial layout as scrna_nmf_wtx_partial with kp = kq = k rounded up to 8.  The factor is
  * passed as its `parts`-part (2 or 3) fp16 operand shadow Fh (scrna_nmf_h_shadow_elems(g, kq, parts) halves,
  * K-major MMA operand layout [(r/8)][n < NB][r%8], n = part*kq + t, NB = scrna_nmf_h_nb) of the factor scaled per
  * component by a power of two; inv_scale[t] (kq floats) undoes the scale when the partial is stored.  Both are
  * written by scrna_nmf_h_shadow / scrna_nmf_update.  x * part is exact in the fp32 accumulator; tensor memory
- * is drained every 512 rows as in the TF32 sweep.  nsplit from scrna_nmf_wtx_h_splits.
- * flags bits 8-23: drain period override in stages of 32 rows. */
+ * is drained every 256 rows into register totals.  nsplit from scrna_nmf_wtx_h_splits.
+ * flags bits 8-23: drain period override in stages of 64 rows. */
 int scrna_nmf_h_supported(int kq);
 int scrna_nmf_h_nb(int kq, int parts);
 int64_t scrna_nmf_h_shadow_elems(int64_t rows, int kq, int parts);
+int64_t scrna_f16_panel_rows(int64_t rows);
+int64_t scrna_f16_panel_elems(int64_t rows, int64_t cols);
 int scrna_nmf_wtx_h_splits(int g, int64_t ncols, int kq, int parts);
-int scrna_nmf_wtx_partial_h(const void* X16, int64_t ldx, int g, int64_t ncols, const void* Fh,
+int scrna_nmf_wtx_partial_h(const void* X16, int64_t rows_pad, int g, int64_t ncols, const void* Fh,
                             const float* inv_scale, int kq, int parts, float* part, int64_t ldc, int nsplit,
                             int flags, const scrna_nmf_ctrl_t* ctrl, void* stream);
-/* Three-part fp16 shadow of a component-major fp64 master (kp-stride Gram partials give the scale):
+/* fp16 operand shadow of a component-major fp64 master (kp-stride Gram partials give the scale):
  * scale_t = 2^e with ||F[:, t]|| * scale_t in [2^12, 2^13), ||.||^2 = sum over the `nblk` partial Grams
  * gram_parts[p*kp*kp + t*kp + t] (nblk = 1: a finished kp x kp Gram).  gram_out != NULL additionally finishes
  * the kp x kp Gram itself (fixed-order sum of the partials) in the same launch. */
@@ -140,11 +146,10 @@ int scrna_nmf_h_shadow(const double* F64, int64_t ld, int64_t rows, int k, int k
                        const scrna_nmf_ctrl_t* ctrl, void* stream);
 /* inexact[0] = 1 if any of the `count` (multiple of 4) fp32 values is not exactly representable in fp16. */
 int scrna_f16_inexact(const float* X, int64_t count, int32_t* inexact, void* stream);
-/* fp32 -> fp16 storage: same layout (padding columns [cols, ld_dst) zeroed), and the transposed copy. */
-int scrna_narrow_f32_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst, int64_t ld_dst,
-                         void* stream);
-int scrna_transpose_f32_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst,
-                            int64_t ld_dst, void* stream);
+/* row-major fp32 (rows x cols, ld_src) -> panel-major fp16 storage of the matrix, and of its transpose
+ * (cols x rows); dst holds scrna_f16_panel_elems(rows, cols) resp. (cols, rows) halves, padding zeroed here. */
+int scrna_narrow_f32_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst, void* stream);
+int scrna_transpose_f32_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst, void* stream);
 
 /* Sum the K1 partials over the splits in fixed order into fp64, component-major: out[t*ld + i]. */
 int scrna_nmf_reduce_rows(const float* part, int nsplit, int g, int kp, double* out, int64_t ld,
@@ -217,8 +222,8 @@ int scrna_convert_pad_f64_f32(const double* src, int64_t ld_src, float* dst, int
 int scrna_residual_blocks(int64_t ncols, int kp);
 int scrna_residual(const float* X, int64_t ldx, int g, int64_t ncols, const float* G32, const float* C32,
                    int64_t ldc, int kp, int power, double* partials, double* out, void* stream);
-/* the same over fp16 storage of X (scrna_narrow_f32_f16) */
-int scrna_residual_h(const void* X16, int64_t ldx, int g, int64_t ncols, const float* G32, const float* C32,
+/* the same over the panel-major fp16 storage of X (scrna_narrow_f32_f16) */
+int scrna_residual_h(const void* X16, int64_t rows_pad, int g, int64_t ncols, const float* G32, const float* C32,
                      int64_t ldc, int kp, int power, double* partials, double* out, void* stream);
 
 /* out[0] = scale * sum(v[0..n)) in a fixed order (block partial sums -> one scalar; used for the

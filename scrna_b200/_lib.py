@@ -54,8 +54,10 @@ _SIGNATURES = {
     "scrna_nmf_h_shadow": [c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                            c_ptr],
     "scrna_f16_inexact": [c_ptr, c_i64, c_ptr, c_ptr],
-    "scrna_narrow_f32_f16": [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr],
-    "scrna_transpose_f32_f16": [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr],
+    "scrna_f16_panel_rows": [c_i64],
+    "scrna_f16_panel_elems": [c_i64, c_i64],
+    "scrna_narrow_f32_f16": [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr],
+    "scrna_transpose_f32_f16": [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr],
     "scrna_residual_h": [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr],
     "scrna_nmf_shadows": [c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr],
     "scrna_transpose_f32": [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr],
@@ -114,10 +116,11 @@ _VALUE_RETURNING = {"scrna_abi_version", "scrna_nmf_xht_splits", "scrna_nmf_wtx_
                     "scrna_nmf_update_blocks", "scrna_residual_blocks", "scrna_nmf_tc_supported", "scrna_nmf_wtx_tc_splits",
                     "scrna_nmf_tc_shadow_elems", "scrna_bjacobi_blocks", "scrna_bjacobi_splits",
                     "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems", "scrna_kta_blocks",
-                    "scrna_nmf_h_supported", "scrna_nmf_h_nb", "scrna_nmf_h_shadow_elems", "scrna_nmf_wtx_h_splits"}
+                    "scrna_nmf_h_supported", "scrna_nmf_h_nb", "scrna_nmf_h_shadow_elems", "scrna_nmf_wtx_h_splits",
+                    "scrna_f16_panel_rows", "scrna_f16_panel_elems"}
 
 
-_RETURNS_I64 = {"scrna_nmf_tc_shadow_elems", "scrna_nmf_h_shadow_elems", "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems"}
+_RETURNS_I64 = {"scrna_nmf_tc_shadow_elems", "scrna_nmf_h_shadow_elems", "scrna_f16_panel_rows", "scrna_f16_panel_elems", "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems"}
 
 
 class ScrnaError(RuntimeError):

@@ -8,33 +8,44 @@
 // iteration has to move (algorithmic bytes 2*g*n*s_X with s_X = 2).  The products stay at fp32
 // accuracy by splitting the small factor instead of X:
 //
-//      s_t * F[:, t] = F1 + F2 + F3      (three fp16 parts, s_t a power of two per component)
-//      F^T.X = (X^T.[F1 | F2 | F3]) summed over the three column groups, unscaled by 1/s_t
+//      s_t * F[:, t] = F1 + F2 (+ F3)    (fp16 parts, s_t a power of two per component)
+//      F^T.X = X^T.[F1 | F2 (| F3)] summed over the column groups, unscaled by 1/s_t
 //
 // x (11 significant bits) times an fp16 part (11 bits) is exact in the fp32 accumulator, so the only rounding
-// is the accumulation itself -- identical in kind to an fp32 FMA chain.  fp16's narrow exponent range is what
-// the per-component scale is for: s_t = 2^e with  ||F[:, t]||_2 * s_t in [2^12, 2^13)  (from the Gram diagonal
-// the epilogue has just produced), so no part can overflow and the absolute representation error of an entry
-// is 2^-25 / s_t <= 2^-37 ||F[:, t]||_2 (three parts: 33 significant bits for entries within 2^-4 of the
-// column norm, tapering below).  tcgen05.mma.kind::f16 does not accept mixed f16 x bf16 operands (measured:
-// illegal instruction, tools/microbench/f16_probe.cu), hence fp16 parts and not a bf16 split.
+// is the accumulation itself -- identical in kind to an fp32 FMA chain.  Two parts carry 22 significant bits of
+// the factor (what the 3xTF32 sweep's [hi | lo] factor split carries; the default), three carry 33.  fp16's
+// narrow exponent range is what the per-component scale is for: s_t = 2^e with ||F[:, t]||_2 * s_t in
+// [2^12, 2^13) (from the Gram diagonal the epilogue has just produced), so no part can overflow and the absolute
+// representation error of an entry is at most 2^-25 / s_t <= 2^-37 ||F[:, t]||_2.  tcgen05.mma.kind::f16 does
+// not accept mixed f16 x bf16 operands (measured: illegal instruction, tools/microbench/f16_probe.cu), hence
+// fp16 parts and not a bf16 split.
+//
+// Storage ("panel-major").  X16 is kept as panels of 256 columns: element (i, j) at
+//      ((j / 256) * rows_pad + i) * 256 + j % 256,      rows_pad = rows rounded up to 64, padding zero,
+// so that the rows a CTA streams are ONE contiguous region of HBM per panel (512 B per row, rows back to back)
+// instead of 1 KB pieces a row pitch apart: measured +3 % of TMA throughput over the row-major layout, and cell
+// shards on several GPUs stream exactly like the full matrix.
 //
 // Mapping.  A CTA owns 128*CM consecutive output columns j (CM = 4 up to rank 40, 2 above) and one span of
 // reduction rows i.  Per 16 rows and per 128-column block m one MMA
-//      D_m[128 lanes][NB] (+)= A_m[128][16] . B[16][NB],          NB = 3*KQ rounded up to 16
+//      D_m[128 lanes][NB] (+)= A_m[128][16] . B[16][NB],          NB = PARTS*KQ rounded up to 16
 //   A (shared memory, MN-major, SWIZZLE_128B): exactly the bytes TMA wrote -- the X tile is staged as boxes of
-//      64 columns x 32 rows (128-byte rows, the swizzle atom), two boxes side by side form the M = 128 operand
+//      64 columns x 64 rows (128-byte rows, the swizzle atom), two boxes side by side form the M = 128 operand
 //      (LBO = box size), 8-row groups are the K atoms (SBO = 1024 B);
 //   B (shared memory, K-major, no swizzle): the factor rows in the canonical layout [(r/8)][n < NB][r%8];
 //   D (tensor memory): lane l of D_m = output column j0 + 128 m + l; column n = part n / KQ of component n % KQ.
-// The accumulator truncates at every accumulation (see nmf_sweep_tc.cu), so it is drained every `drain`
-// stages (512 rows) into fp32 running totals in shared memory; two accumulator sets alternate when tensor
-// memory has room (rank <= 16), so the MMA stream never waits for a drain.
+// The tensor core truncates its fp32 accumulator at every accumulation (see nmf_sweep_tc.cu; measured here:
+// a relative bias of ~1.6e-7 per MMA of the chain), so the accumulators are drained every `drain` stages
+// (256 rows) into fp32 running totals held in REGISTERS (one output column per thread and m); two accumulator
+// sets alternate in tensor memory, so the MMA stream never waits for a drain.
 //
-// Pipeline (192 threads, one CTA per SM):
+// Pipeline (192 threads, one CTA per SM, a stage = 64 rows: 64 KB of X at CM = 4):
 //      warp 4 lane 0 : TMA producer (NBOX tensor boxes + one bulk copy of the factor block per stage);
-//      warp 5 lane 0 : MMA issuer (CM * 2 MMAs per stage, tcgen05.commit to "slot free" / "accumulators full");
-//      warps 0-3     : drain tensor memory -> totals -> (last period) unscale and store the split partial.
+//      warp 5 lane 0 : MMA issuer (CM * 4 MMAs per stage, tcgen05.commit to "slot free" / "accumulators full");
+//      warps 0-3     : drain tensor memory -> register totals -> (end of span) unscale and store the partial.
+// Measured on the way (tools/microbench/f16_probe.cu, profiles/r02_f16_sweep_experiments.md): 64-row stages beat
+// 32-row stages by 4 %; an L2 prefetcher running 4-14 stages ahead of the ring LOSES 3-30 % (the stream is
+// bandwidth- not latency-bound); two co-resident CTAs per SM on 256-column tiles are neutral.
 //
 // Algorithmic bytes per launch: rows * ncols * 2 (X once) + rows * NB * 2 per column tile (factor, from L2).
 #include <cuda_fp16.h>
@@ -44,35 +55,31 @@
 
 namespace scrna {
 
-constexpr int H_THREADS = 224;  // 4 drain warps + producer + MMA issuer + L2 prefetcher
-constexpr int H_ALIGN = 64;     // row spans and operand shadows are padded to this many rows
+constexpr int H_THREADS = 192;  // 4 drain warps + producer + MMA issuer
+constexpr int H_ALIGN = 64;     // row spans, panels and operand shadows are padded to this many rows
+constexpr int H_SR = 64;        // rows per pipeline stage = TMA box height = four K = 16 MMA steps
+constexpr int H_PANEL = 256;    // columns per storage panel
 
-// SR = rows per pipeline stage = TMA box height (32 or 64: two or four K = 16 MMA steps)
-template <int KQ, int PARTS, int OCC = 1, int SR = 32>
+template <int KQ, int PARTS>
 struct HCfg {
-  static_assert(SR == 32 || SR == 64, "stage height");
   static_assert(KQ % 8 == 0 && KQ >= 8 && KQ <= 64, "component groups are padded to multiples of 8");
   static_assert(PARTS == 2 || PARTS == 3, "two- or three-part fp16 split of the factor");
   static constexpr int NB = ((PARTS * KQ + 15) / 16) * 16;   // MMA N: [F1 | F2 (| F3) | zero pad]
-  // 128-column MMA blocks per CTA: 4 while the accumulators fit tensor memory and the running totals leave room
-  // for a 3-stage ring in shared memory, else 2
-  static constexpr int CM =
-      (OCC == 1 && 4 * NB <= 512 && (224 * 1024 - KQ * 2048) / (8 * SR * 128 + NB * 2 * SR) >= 3) ? 4 : 2;
-  static constexpr int SMEM_BUDGET = OCC == 1 ? 224 * 1024 : 110 * 1024;   // OCC CTAs share an SM
-  static constexpr int TMEM_COLS = OCC == 1 ? 512 : 256;
+  // 128-column MMA blocks per CTA: 4 while the accumulators fit tensor memory, the register totals (CM * KQ
+  // floats per drain thread) fit the register file and three 64-row stages fit shared memory, else 2
+  static constexpr int CM = (4 * NB <= 512 && KQ <= 40 && 3 * (8 * H_SR * 128 + NB * 2 * H_SR) <= 226 * 1024 - 256) ? 4 : 2;
   static constexpr int COLS = 128 * CM;
-  static constexpr int KSTEPS = SR / 16;
-  static constexpr int BOX_BYTES = SR * 128;             // 64 fp16 columns x SR rows
+  static constexpr int KSTEPS = H_SR / 16;
+  static constexpr int BOX_BYTES = H_SR * 128;           // 64 fp16 columns x 64 rows
   static constexpr int NBOX = COLS / 64;
   static constexpr int XBYTES = NBOX * BOX_BYTES;
   static constexpr int BSTEP = NB * 32;                  // factor rows of one K-step: 2 chunks x NB x 16 B
   static constexpr int BBYTES = KSTEPS * BSTEP;
   static constexpr int STAGE_BYTES = XBYTES + BBYTES;    // multiple of 1024 (NB % 16 == 0)
-  static constexpr int TOTAL_BYTES = KQ * COLS * 4;
-  static constexpr int NACC = (2 * CM * NB <= TMEM_COLS) ? 2 : 1;
-  static constexpr int NS_FIT = (SMEM_BUDGET - TOTAL_BYTES) / STAGE_BYTES;
-  static constexpr int NS = NS_FIT > 8 ? 8 : NS_FIT;
-  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + TOTAL_BYTES + 1024;
+  static constexpr int NACC = (2 * CM * NB <= 512) ? 2 : 1;
+  static constexpr int NS_FIT = (226 * 1024 - 256) / STAGE_BYTES;
+  static constexpr int NS = NS_FIT > 6 ? 6 : NS_FIT;
+  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + 1024;
   static_assert(NS >= 3, "need a pipelined shared-memory ring");
   static_assert(STAGE_BYTES % 1024 == 0, "swizzled boxes need 1024-byte aligned stage bases");
 };
@@ -92,14 +99,14 @@ __device__ __forceinline__ uint64_t h_smem_desc(uint32_t saddr, uint32_t lbo_byt
          (1ull << 46) | ((uint64_t)layout << 61);
 }
 
-// flags: bits 5-7 = L2 prefetch distance in units of two stages (0 = off);
-// bring-up probes only: 1 = no MMAs, 2 = no factor copies, 4 = no X copies
-template <int KQ, int PARTS, int OCC, int SR>
-__global__ void __launch_bounds__(H_THREADS, OCC)
-wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int64_t ncols, const __half* __restrict__ Fh,
-             const float* __restrict__ inv_scale, float* __restrict__ part, int64_t ldc, int rows_per_split, int drain,
-             int flags, const NmfCtrl* __restrict__ ctrl) {
-  using Cfg = HCfg<KQ, PARTS, OCC, SR>;
+// xmap: 2-D tensor map over the panel-major storage viewed as (npanels * rows_pad) rows of 256 columns.
+// flags (bring-up probes only): 1 = no MMAs, 2 = no factor copies, 4 = no X copies
+template <int KQ, int PARTS>
+__global__ void __launch_bounds__(H_THREADS, 1)
+wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int rows_pad, int64_t ncols,
+             const __half* __restrict__ Fh, const float* __restrict__ inv_scale, float* __restrict__ part, int64_t ldc,
+             int rows_per_split, int drain, int flags, const NmfCtrl* __restrict__ ctrl) {
+  using Cfg = HCfg<KQ, PARTS>;
   constexpr int NB = Cfg::NB, CM = Cfg::CM, NS = Cfg::NS, NACC = Cfg::NACC;
   if (ctrl_done(ctrl)) return;
   extern __shared__ uint8_t h_smem_raw[];
@@ -117,7 +124,7 @@ wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int64_t ncols, con
   const int r_begin = blockIdx.y * rows_per_split;
   int r_end = r_begin + rows_per_split;
   if (r_end > g) r_end = g;
-  const int nstages = r_end > r_begin ? (r_end - r_begin + SR - 1) / SR : 0;
+  const int nstages = r_end > r_begin ? (r_end - r_begin + H_SR - 1) / H_SR : 0;
   const int nperiods = (nstages + drain - 1) / drain;
 
   if (tid == 0) {
@@ -133,7 +140,7 @@ wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int64_t ncols, con
   }
   if (warp == 5) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -143,40 +150,24 @@ wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int64_t ncols, con
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 4) {
-    // ===== TMA producer.  Rows past g and columns past ncols are zero-filled by the tensor map; spans are
-    // multiples of the stage height, so a stage never straddles two spans.
+    // ===== TMA producer.  Spans are multiples of the stage height and the storage is zero-padded to whole
+    // stages and panels, so a stage never straddles two spans; a panel past the matrix reads as zeros.
     if (lane == 0) {
+      const int panel0 = (int)(col0 / H_PANEL);
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nstages; ++i) {
-        const int r0 = r_begin + i * SR;
+        const int r0 = r_begin + i * H_SR;
         const uint32_t dst = smem_base + s * Cfg::STAGE_BYTES;
         const uint32_t bar = full_x + 8 * s;
         mbar_wait(empty_x + 8 * s, ph ^ 1u);
         mbar_expect_tx(bar, ((flags & 4) ? 0u : (uint32_t)Cfg::XBYTES) + ((flags & 2) ? 0u : (uint32_t)Cfg::BBYTES));
         if (!(flags & 4)) {
 #pragma unroll
-          for (int b = 0; b < Cfg::NBOX; ++b) tma_load_2d(dst + b * Cfg::BOX_BYTES, &xmap, (int)col0 + b * 64, r0, bar);
+          for (int b = 0; b < Cfg::NBOX; ++b)
+            tma_load_2d(dst + b * Cfg::BOX_BYTES, &xmap, (b & 3) * 64, (panel0 + (b >> 2)) * rows_pad + r0, bar);
         }
         if (!(flags & 2)) bulk_g2s(dst + Cfg::XBYTES, Fh + (int64_t)r0 * NB, Cfg::BBYTES, bar);
-        if (++s == NS) { s = 0; ph ^= 1u; }
-      }
-    }
-  } else if (warp == 6) {
-    // ===== L2 prefetcher: keeps `ahead - NS` stages beyond the shared-memory ring in flight towards L2, so that the
-    // ring only has to cover the L2 latency.  A hint only: the waits are bounded and never trap.
-    const int dist = (flags >> 5) & 7;
-    if (lane == 0 && dist > 0) {
-      const int ahead = NS + 2 * dist;
-      for (int i = NS; i < ahead && i < nstages; ++i)
-#pragma unroll
-        for (int b = 0; b < Cfg::NBOX; ++b) tma_prefetch_2d(&xmap, (int)col0 + b * 64, r_begin + i * SR);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i + ahead < nstages; ++i) {
-        for (int spin = 0; spin < 2000 && !mbar_try_wait(full_x + 8 * s, ph); ++spin) {}
-#pragma unroll
-        for (int b = 0; b < Cfg::NBOX; ++b) tma_prefetch_2d(&xmap, (int)col0 + b * 64, r_begin + (i + ahead) * SR);
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
     }
@@ -218,20 +209,22 @@ wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int64_t ncols, con
       }
     }
   } else {
-    // ===== drain warps (0-3): warp w reads tensor-memory lanes 32w .. 32w+31 =====
+    // ===== drain warps (0-3): warp w reads tensor-memory lanes 32w .. 32w+31; thread tid owns output columns
+    // col0 + 128 m + tid and keeps their running totals in registers =====
     const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
-    float* const totals = reinterpret_cast<float*>(h_smem_raw + (smem_base - smem_u32(h_smem_raw)) + NS * Cfg::STAGE_BYTES);
-    float* const out = part + ((int64_t)blockIdx.y * KQ) * ldc + col0 + tid;
+    float tot[CM][KQ];
+#pragma unroll
+    for (int m = 0; m < CM; ++m)
+#pragma unroll
+      for (int t = 0; t < KQ; ++t) tot[m][t] = 0.f;
     for (int p = 0; p < nperiods; ++p) {
       const int buf = p % NACC;
-      const bool final_drain = p + 1 == nperiods;
       mbar_wait(acc_full + 8 * buf, (uint32_t)((p / NACC) & 1));
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int m = 0; m < CM; ++m) {
         const uint32_t acc = tmem_base + lane_field + (buf * CM + m) * NB;
-        const bool in_range = col0 + m * 128 + tid < ncols;
-#pragma unroll 1
+#pragma unroll
         for (int t0 = 0; t0 < KQ; t0 += 8) {
           float a[8], b[8], c[8];
           tc_ld8(acc + t0, a);
@@ -243,20 +236,19 @@ wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int64_t ncols, con
             mbar_arrive(acc_empty + 8 * buf);
           }
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            float v = PARTS == 3 ? (c[t] + b[t]) + a[t] : b[t] + a[t];  // smallest parts first
-            float* slot = totals + (t0 + t) * Cfg::COLS + m * 128 + tid;
-            if (p > 0) v += *slot;
-            if (!final_drain) *slot = v;
-            else if (in_range) out[(int64_t)(t0 + t) * ldc + m * 128] = v * (inv_scale ? __ldg(inv_scale + t0 + t) : 1.f);
-          }
+          for (int t = 0; t < 8; ++t)  // smallest parts first
+            tot[m][t0 + t] += PARTS == 3 ? (c[t] + b[t]) + a[t] : b[t] + a[t];
         }
       }
     }
-    if (nstages == 0) {
-      for (int m = 0; m < CM; ++m)
-        if (col0 + m * 128 + tid < ncols)
-          for (int t = 0; t < KQ; ++t) out[(int64_t)t * ldc + m * 128] = 0.f;
+    float* const out = part + ((int64_t)blockIdx.y * KQ) * ldc + col0 + tid;
+#pragma unroll
+    for (int m = 0; m < CM; ++m) {
+      if (col0 + m * 128 + tid < ncols) {
+#pragma unroll
+        for (int t = 0; t < KQ; ++t)
+          out[(int64_t)t * ldc + m * 128] = tot[m][t] * (inv_scale ? __ldg(inv_scale + t) : 1.f);
+      }
     }
   }
 
@@ -264,15 +256,14 @@ wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int64_t ncols, con
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
-                 : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
 // ---- operand shadow ---------------------------------------------------------------------------------------
 // CTAs [0, row_ctas): finish the per-component scale from the Gram diagonal (sum over `nblk` block partials in
 // fixed order -- every CTA computes the same numbers) and split the factor into its three fp16 parts, K-major
-// canonical layout out[((r/8) * NB + n) * 8 + r%8], n = part * KQ + t; rows padded to 32.  A thread owns one
+// canonical layout out[((r/8) * NB + n) * 8 + r%8], n = part * KQ + t; rows padded to 64.  A thread owns one
 // (8-row group, component) pair: it reads 64 contiguous bytes of the master and writes three 16-byte vectors,
 // consecutive threads writing consecutive vectors.
 // CTAs [row_ctas, ...): the k x k Gram itself (one warp per entry), i.e. gram_final_kernel folded into the same
@@ -352,23 +343,23 @@ __global__ void f16_exact_kernel(const float4* __restrict__ X, int64_t n4, int* 
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(inexact, 1);
 }
 
-// dst[r][c] = (half)src[r][c], padding columns [cols, ld_dst) zero
+// panel-major fp16 storage of a row-major fp32 matrix: dst[((c / 256) * rows_pad + r) * 256 + c % 256];
+// padding (rows >= rows, columns >= cols) is zeroed by the caller
 __global__ void narrow_f16_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int64_t cols,
-                                  __half* __restrict__ dst, int64_t ld_dst) {
+                                  __half* __restrict__ dst, int64_t rows_pad) {
   const int64_t r = blockIdx.y;
   const float* s = src + r * ld_src;
-  __half* d = dst + r * ld_dst;
-  for (int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; c < ld_dst;
+  for (int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; c < cols;
        c += (int64_t)gridDim.x * blockDim.x * 2) {
-    const float a = c < cols ? s[c] : 0.f, b = c + 1 < cols ? s[c + 1] : 0.f;
-    *reinterpret_cast<__half2*>(d + c) = __floats2half2_rn(a, b);
+    const float a = s[c], b = c + 1 < cols ? s[c + 1] : 0.f;
+    *reinterpret_cast<__half2*>(dst + ((c >> 8) * rows_pad + r) * H_PANEL + (c & 255)) = __floats2half2_rn(a, b);
   }
 }
 
-// dst[c][r] = (half)src[r][c]; dst padding columns [rows, ld_dst) zeroed by the caller
+// the transposed copy in the same storage: element (c, r) of X^T, i.e. dst[((r / 256) * cols_pad + c) * 256 + r % 256]
 __global__ void __launch_bounds__(256)
 transpose_f16_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int64_t cols,
-                     __half* __restrict__ dst, int64_t ld_dst) {
+                     __half* __restrict__ dst, int64_t cols_pad) {
   __shared__ float tile[64][65];
   const int64_t c0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
@@ -381,31 +372,33 @@ transpose_f16_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows
   const int px = threadIdx.x & 31, py = threadIdx.x >> 5;  // 32 row pairs x 8
 #pragma unroll
   for (int i = 0; i < 64; i += 8) {
-    const int64_t c = c0 + py + i, r = r0 + 2 * px;
+    const int64_t c = c0 + py + i, r = r0 + 2 * px;  // r even: the pair stays inside one panel
     if (c < cols && r < rows)
-      *reinterpret_cast<__half2*>(dst + c * ld_dst + r) = __floats2half2_rn(tile[2 * px][py + i], tile[2 * px + 1][py + i]);
+      *reinterpret_cast<__half2*>(dst + ((r >> 8) * cols_pad + c) * H_PANEL + (r & 255)) =
+          __floats2half2_rn(tile[2 * px][py + i], tile[2 * px + 1][py + i]);
   }
 }
 
-template <int KQ, int PARTS, int OCC, int SR>
-static int wtx_h_launch(const __half* X, int64_t ldx, int g, int64_t ncols, const __half* Fh, const float* inv_scale,
+template <int KQ, int PARTS>
+static int wtx_h_launch(const __half* X, int64_t rows_pad, int g, int64_t ncols, const __half* Fh, const float* inv_scale,
                         float* part, int64_t ldc, int nsplit, int rps, int drain, int flags, const NmfCtrl* ctrl,
                         cudaStream_t st) {
-  using Cfg = HCfg<KQ, PARTS, OCC, SR>;
+  using Cfg = HCfg<KQ, PARTS>;
   CUtensorMap xmap;
-  if (int rc = make_tensor_map_2d(&xmap, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ldx, g, ncols, 64, SR,
-                                  CU_TENSOR_MAP_SWIZZLE_128B))
+  const int64_t npanels = ceil_div(ncols, H_PANEL);
+  if (int rc = make_tensor_map_2d(&xmap, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, H_PANEL, npanels * rows_pad, H_PANEL, 64,
+                                  H_SR, CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
-        cudaFuncSetAttribute(wtx_h_kernel<KQ, PARTS, OCC, SR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaFuncSetAttribute(wtx_h_kernel<KQ, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return SCRNA_ERR_CUDA;
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(ncols, Cfg::COLS), (unsigned)nsplit);
-  wtx_h_kernel<KQ, PARTS, OCC, SR><<<grid, H_THREADS, Cfg::SMEM_BYTES, st>>>(xmap, g, ncols, Fh, inv_scale, part, ldc, rps,
-                                                                       drain / (SR / 32), flags, ctrl);
+  wtx_h_kernel<KQ, PARTS><<<grid, H_THREADS, Cfg::SMEM_BYTES, st>>>(xmap, g, (int)rows_pad, ncols, Fh, inv_scale, part, ldc,
+                                                                   rps, drain, flags, ctrl);
   return last_launch_status();
 }
 
@@ -417,15 +410,15 @@ static int h_rows_per_split(int g, int nsplit) {
 static int h_nb(int kq, int parts) { return ((parts * kq + 15) / 16) * 16; }
 static int h_cols_per_cta(int kq, int parts) {
   const int nb = h_nb(kq, parts);
-  return (4 * nb <= 512 && (224 * 1024 - kq * 2048) / (8 * 32 * 128 + nb * 64) >= 3) ? 512 : 256;
+  return (4 * nb <= 512 && kq <= 40 && 3 * (8 * H_SR * 128 + nb * 2 * H_SR) <= 226 * 1024 - 256) ? 512 : 256;
 }
 
 }  // namespace scrna
 
 using namespace scrna;
 
-#define SCRNA_DISPATCH_H(kq, ...)                    \
-  switch (kq) {                                      \
+#define SCRNA_DISPATCH_H(kq, ...)                           \
+  switch (kq) {                                             \
     case 8: { constexpr int KQ = 8; __VA_ARGS__; } break;   \
     case 16: { constexpr int KQ = 16; __VA_ARGS__; } break; \
     case 24: { constexpr int KQ = 24; __VA_ARGS__; } break; \
@@ -434,7 +427,7 @@ using namespace scrna;
     case 48: { constexpr int KQ = 48; __VA_ARGS__; } break; \
     case 56: { constexpr int KQ = 56; __VA_ARGS__; } break; \
     case 64: { constexpr int KQ = 64; __VA_ARGS__; } break; \
-    default: return SCRNA_ERR_UNSUPPORTED;           \
+    default: return SCRNA_ERR_UNSUPPORTED;                  \
   }
 
 extern "C" int scrna_nmf_h_supported(int kq) { return (kq >= 8 && kq <= 64 && (kq & 7) == 0) ? 1 : 0; }
@@ -446,6 +439,13 @@ extern "C" int scrna_nmf_h_nb(int kq, int parts) {
 extern "C" int64_t scrna_nmf_h_shadow_elems(int64_t rows, int kq, int parts) {
   if (!scrna_nmf_h_supported(kq) || rows <= 0 || (parts != 2 && parts != 3)) return SCRNA_ERR_BADARG;
   return ceil_div(rows, H_ALIGN) * H_ALIGN * (int64_t)h_nb(kq, parts);
+}
+
+extern "C" int64_t scrna_f16_panel_rows(int64_t rows) { return rows > 0 ? ceil_div(rows, H_ALIGN) * H_ALIGN : SCRNA_ERR_BADARG; }
+
+extern "C" int64_t scrna_f16_panel_elems(int64_t rows, int64_t cols) {
+  if (rows <= 0 || cols <= 0) return SCRNA_ERR_BADARG;
+  return ceil_div(cols, H_PANEL) * scrna_f16_panel_rows(rows) * H_PANEL;
 }
 
 extern "C" int scrna_nmf_wtx_h_splits(int g, int64_t ncols, int kq, int parts) {
@@ -471,30 +471,27 @@ extern "C" int scrna_nmf_wtx_h_splits(int g, int64_t ncols, int kq, int parts) {
   return best;
 }
 
-extern "C" int scrna_nmf_wtx_partial_h(const void* X16, int64_t ldx, int g, int64_t ncols, const void* Fh,
+extern "C" int scrna_nmf_wtx_partial_h(const void* X16, int64_t rows_pad, int g, int64_t ncols, const void* Fh,
                                        const float* inv_scale, int kq, int parts, float* part, int64_t ldc, int nsplit,
                                        int flags, const scrna_nmf_ctrl_t* ctrl, void* stream) {
-  if (!X16 || !Fh || !part || g <= 0 || ncols <= 0 || nsplit <= 0 || (ldx & 7) || ncols > ldx || ncols > ldc ||
-      (reinterpret_cast<uintptr_t>(X16) & 15) || (parts != 2 && parts != 3))
+  if (!X16 || !Fh || !part || g <= 0 || ncols <= 0 || nsplit <= 0 || rows_pad < g || (rows_pad % H_ALIGN) ||
+      ncols > ldc || (reinterpret_cast<uintptr_t>(X16) & 127) || (parts != 2 && parts != 3) ||
+      ceil_div(ncols, H_PANEL) * rows_pad > 0x7fffffffLL)
     return SCRNA_ERR_BADARG;
   const int rps = h_rows_per_split(g, nsplit);
   if ((int64_t)rps * (nsplit - 1) >= g && nsplit > 1) return SCRNA_ERR_BADARG;  // an empty span
-  int drain = (flags >> 8) & 0xffff;  // tuning override of the drain period (stages of 32 rows)
-  if (drain <= 0) drain = 16;         // 512 rows
+  int drain = (flags >> 8) & 0xffff;  // tuning override of the drain period (stages of 64 rows)
+  if (drain <= 0) drain = 4;          // 256 rows
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const NmfCtrl* c = reinterpret_cast<const NmfCtrl*>(ctrl);
   const __half* Xh = reinterpret_cast<const __half*>(X16);
   const __half* F = reinterpret_cast<const __half*>(Fh);
-  if ((flags & 8) && kq == 8 && parts == 3)  // experiment: two co-resident CTAs per SM on 256-column tiles
-    return wtx_h_launch<8, 3, 2, 32>(Xh, ldx, g, ncols, F, inv_scale, part, ldc, nsplit, rps, drain, flags & 0xff, c, st);
-  if ((flags & 16) && kq == 8 && parts == 3)  // experiment: 64-row stages
-    return wtx_h_launch<8, 3, 1, 64>(Xh, ldx, g, ncols, F, inv_scale, part, ldc, nsplit, rps, drain, flags & 0xff, c, st);
   if (parts == 2) {
-    SCRNA_DISPATCH_H(kq, return (wtx_h_launch<KQ, 2, 1, 32>(Xh, ldx, g, ncols, F, inv_scale, part, ldc, nsplit, rps, drain,
-                                                            flags & 0xff, c, st)));
+    SCRNA_DISPATCH_H(kq, return (wtx_h_launch<KQ, 2>(Xh, rows_pad, g, ncols, F, inv_scale, part, ldc, nsplit, rps, drain,
+                                                     flags & 0xff, c, st)));
   } else {
-    SCRNA_DISPATCH_H(kq, return (wtx_h_launch<KQ, 3, 1, 32>(Xh, ldx, g, ncols, F, inv_scale, part, ldc, nsplit, rps, drain,
-                                                            flags & 0xff, c, st)));
+    SCRNA_DISPATCH_H(kq, return (wtx_h_launch<KQ, 3>(Xh, rows_pad, g, ncols, F, inv_scale, part, ldc, nsplit, rps, drain,
+                                                     flags & 0xff, c, st)));
   }
   return SCRNA_ERR_UNSUPPORTED;
 }
@@ -523,27 +520,32 @@ extern "C" int scrna_f16_inexact(const float* X, int64_t count, int32_t* inexact
 }
 
 extern "C" int scrna_narrow_f32_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst,
-                                    int64_t ld_dst, void* stream) {
-  if (!src || !dst || rows <= 0 || cols <= 0 || cols > ld_src || cols > ld_dst || (ld_dst & 1)) return SCRNA_ERR_BADARG;
+                                    void* stream) {
+  if (!src || !dst || rows <= 0 || cols <= 0 || cols > ld_src) return SCRNA_ERR_BADARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t rows_pad = scrna_f16_panel_rows(rows);
+  if (cudaMemsetAsync(dst, 0, (size_t)scrna_f16_panel_elems(rows, cols) * 2, st) != cudaSuccess) return SCRNA_ERR_CUDA;
   for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
     const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
-    int bx = (int)ceil_div(ld_dst, 512);
+    int bx = (int)ceil_div(cols, 512);
     if (bx > 64) bx = 64;
     dim3 grid((unsigned)bx, (unsigned)nr);
     narrow_f16_kernel<<<grid, 256, 0, st>>>(src + r0 * ld_src, ld_src, nr, cols,
-                                            reinterpret_cast<__half*>(dst) + r0 * ld_dst, ld_dst);
+                                            reinterpret_cast<__half*>(dst) + r0 * H_PANEL, rows_pad);
   }
   return last_launch_status();
 }
 
 extern "C" int scrna_transpose_f32_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst,
-                                       int64_t ld_dst, void* stream) {
-  if (!src || !dst || rows <= 0 || cols <= 0 || cols > ld_src || rows > ld_dst || (ld_dst & 1)) return SCRNA_ERR_BADARG;
+                                       void* stream) {
+  if (!src || !dst || rows <= 0 || cols <= 0 || cols > ld_src) return SCRNA_ERR_BADARG;
   const int64_t by = ceil_div(rows, 64);
   if (by > 65535) return SCRNA_ERR_UNSUPPORTED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // the transposed matrix has `cols` rows and `rows` columns
+  if (cudaMemsetAsync(dst, 0, (size_t)scrna_f16_panel_elems(cols, rows) * 2, st) != cudaSuccess) return SCRNA_ERR_CUDA;
   dim3 grid((unsigned)ceil_div(cols, 64), (unsigned)by);
-  transpose_f16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, ld_src, rows, cols, reinterpret_cast<__half*>(dst), ld_dst);
+  transpose_f16_kernel<<<grid, 256, 0, st>>>(src, ld_src, rows, cols, reinterpret_cast<__half*>(dst),
+                                             scrna_f16_panel_rows(cols));
   return last_launch_status();
 }

@@ -43,7 +43,7 @@ transfer_mu_step_kernel(double* __restrict__ H64, float* __restrict__ H32, const
 // registers, and the gene-factor rows are broadcast from shared memory.
 template <typename XT, int KP, int C, int POWER>
 __global__ void __launch_bounds__(256, 2)
-residual_kernel(const XT* __restrict__ X, int64_t ldx, int g, int64_t ncols,
+residual_kernel(const XT* __restrict__ X, int64_t ldx, int64_t panel_stride, int g, int64_t ncols,
                 const float* __restrict__ G32, const float* __restrict__ C32, int64_t ldc,
                 int rows_per_split, int tile_rows, double* __restrict__ partials) {
   extern __shared__ float4 smem4[];
@@ -81,7 +81,8 @@ residual_kernel(const XT* __restrict__ X, int64_t ldx, int g, int64_t ncols,
     }
     __syncthreads();
     if (!active) continue;
-    const XT* xr = X + (int64_t)t0 * ldx + j0;
+    // row-major: element (i, j) at i*ldx + j; panel-major (panel_stride != 0, ldx = 256): panels of 256 columns
+    const XT* xr = X + (int64_t)t0 * ldx + (panel_stride ? (j0 >> 8) * panel_stride + (j0 & 255) : j0);
     float part = 0.f;  // fp32 within a tile (<= a few thousand terms), fp64 across tiles
     for (int r = 0; r < nr; r += U) {
       Vec<C> xa[U];
@@ -238,7 +239,7 @@ struct ResCfg {
 };
 
 template <typename XT, int KP>
-static int residual_launch(const XT* X, int64_t ldx, int g, int64_t ncols, const float* G32,
+static int residual_launch(const XT* X, int64_t ldx, int64_t panel_stride, int g, int64_t ncols, const float* G32,
                            const float* C32, int64_t ldc, int power, double* partials, double* out,
                            int nsplit, cudaStream_t st) {
   constexpr int C = ResCfg<KP>::C;
@@ -250,9 +251,11 @@ static int residual_launch(const XT* X, int64_t ldx, int g, int64_t ncols, const
   dim3 grid((unsigned)ceil_div(ncols, 8 * 32 * C), (unsigned)nsplit);
   const size_t smem = (size_t)tr * KP * sizeof(float);
   if (power == 1)
-    residual_kernel<XT, KP, C, 1><<<grid, 256, smem, st>>>(X, ldx, g, ncols, G32, C32, ldc, rps, tr, partials);
+    residual_kernel<XT, KP, C, 1><<<grid, 256, smem, st>>>(X, ldx, panel_stride, g, ncols, G32, C32, ldc, rps, tr,
+                                                           partials);
   else
-    residual_kernel<XT, KP, C, 2><<<grid, 256, smem, st>>>(X, ldx, g, ncols, G32, C32, ldc, rps, tr, partials);
+    residual_kernel<XT, KP, C, 2><<<grid, 256, smem, st>>>(X, ldx, panel_stride, g, ncols, G32, C32, ldc, rps, tr,
+                                                           partials);
   sum_partials_kernel<<<1, 256, 0, st>>>(partials, (int)(grid.x * grid.y), out, 1.0);
   return last_launch_status();
 }
@@ -301,23 +304,23 @@ extern "C" int scrna_residual(const float* X, int64_t ldx, int g, int64_t ncols,
   cudaStream_t st = (cudaStream_t)stream;
   SCRNA_DISPATCH_KP_T(kp, {
     const int64_t tiles = ceil_div(ncols, 8 * 32 * ResCfg<KP>::C);
-    return residual_launch<float, KP>(X, ldx, g, ncols, G32, C32, ldc, power, partials, out,
+    return residual_launch<float, KP>(X, ldx, 0, g, ncols, G32, C32, ldc, power, partials, out,
                                       residual_splits(g, tiles), st);
   });
   return SCRNA_ERR_UNSUPPORTED;
 }
 
-extern "C" int scrna_residual_h(const void* X16, int64_t ldx, int g, int64_t ncols, const float* G32,
+extern "C" int scrna_residual_h(const void* X16, int64_t rows_pad, int g, int64_t ncols, const float* G32,
                                 const float* C32, int64_t ldc, int kp, int power, double* partials,
                                 double* out, void* stream) {
-  if (!X16 || !G32 || !C32 || !partials || !out || g <= 0 || ncols <= 0 || (ldx & 3) || (ldc & 3) ||
-      (ncols & 3) || ncols > ldx || ncols > ldc || (power != 1 && power != 2))
+  if (!X16 || !G32 || !C32 || !partials || !out || g <= 0 || ncols <= 0 || rows_pad < g || (ldc & 3) ||
+      (ncols & 3) || ncols > ldc || (power != 1 && power != 2))
     return SCRNA_ERR_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   SCRNA_DISPATCH_KP_T(kp, {
     const int64_t tiles = ceil_div(ncols, 8 * 32 * ResCfg<KP>::C);
-    return residual_launch<__half, KP>(reinterpret_cast<const __half*>(X16), ldx, g, ncols, G32, C32, ldc, power,
-                                       partials, out, residual_splits(g, tiles), st);
+    return residual_launch<__half, KP>(reinterpret_cast<const __half*>(X16), 256, rows_pad * 256, g, ncols, G32, C32,
+                                       ldc, power, partials, out, residual_splits(g, tiles), st);
   });
   return SCRNA_ERR_UNSUPPORTED;
 }

@@ -90,13 +90,19 @@ class CudaKernels:
     def wtx_h_splits(self, g, ncols, kq, parts):
         return _lib.call("scrna_nmf_wtx_h_splits", g, ncols, kq, parts)
 
-    def wtx_partial_h(self, X16, ldx, g, ncols, Fh, inv_scale, kq, parts, part, ldc, nsplit, ctrl, flags=0):
+    def panel_rows(self, rows):
+        return _lib.call("scrna_f16_panel_rows", rows)
+
+    def panel_elems(self, rows, cols):
+        return _lib.call("scrna_f16_panel_elems", rows, cols)
+
+    def wtx_partial_h(self, X16, rows_pad, g, ncols, Fh, inv_scale, kq, parts, part, ldc, nsplit, ctrl, flags=0):
         ev = self.sweep_events
         if ev is not None:
             a = self.torch.cuda.Event(enable_timing=True)
             b = self.torch.cuda.Event(enable_timing=True)
             a.record()
-        self._call("scrna_nmf_wtx_partial_h", X16, ldx, g, ncols, Fh, inv_scale, kq, parts, part, ldc, nsplit,
+        self._call("scrna_nmf_wtx_partial_h", X16, rows_pad, g, ncols, Fh, inv_scale, kq, parts, part, ldc, nsplit,
                    flags | self.h_flags, ctrl, self._s())
         if ev is not None:
             b.record()
@@ -112,11 +118,11 @@ class CudaKernels:
         self._call("scrna_f16_inexact", X, X.numel(), flag, self._s())
         return int(flag.item()) == 0
 
-    def narrow_f16(self, src, ld_src, rows, cols, dst, ld_dst):
-        self._call("scrna_narrow_f32_f16", src, ld_src, rows, cols, dst, ld_dst, self._s())
+    def narrow_f16(self, src, ld_src, rows, cols, dst):
+        self._call("scrna_narrow_f32_f16", src, ld_src, rows, cols, dst, self._s())
 
-    def transpose_f16(self, src, ld_src, rows, cols, dst, ld_dst):
-        self._call("scrna_transpose_f32_f16", src, ld_src, rows, cols, dst, ld_dst, self._s())
+    def transpose_f16(self, src, ld_src, rows, cols, dst):
+        self._call("scrna_transpose_f32_f16", src, ld_src, rows, cols, dst, self._s())
 
     def tf32_exact(self, X):
         """True if every element of the fp32 tensor is exactly representable in TF32."""
@@ -166,7 +172,7 @@ class CudaKernels:
 
     def residual(self, X, ldx, g, ncols, G32, C32, ldc, kp, power, partials, out):
         self.launches += 1
-        name = "scrna_residual_h" if X.dtype == self.torch.float16 else "scrna_residual"
+        name = "scrna_residual_h" if X.dtype == self.torch.float16 else "scrna_residual"   # ldx = rows_pad for fp16
         self._call(name, X, ldx, g, ncols, G32, C32, ldc, kp, power, partials, out, self._s())
 
     def sum_f64(self, v, n, out, scale=1.0):

@@ -28,7 +28,7 @@ import numpy as np
 from . import _lib
 
 
-H_PARTS = 3   # fp16 parts of the factor in the 16-bit sweep (3: 33 significant bits; 2: 22, as the 3xTF32 sweep)
+H_PARTS = 2   # fp16 parts of the factor in the 16-bit sweep (2: 22 significant bits, as the 3xTF32 sweep; 3: 33)
 
 
 def round_up(a, m):
@@ -63,13 +63,15 @@ class DeviceMatrix:
     def __init__(self, data, n, tf32_exact=None, f16_exact=None):
         self.tf32_exact = tf32_exact   # every element representable in TF32 (raw counts < 2048): lazily probed
         self.f16_exact = f16_exact     # every element representable in fp16 (raw counts <= 2048): lazily probed
-        self._half = None              # fp16 twin of an fp32 matrix (16-bit storage path), built once
+        self._half = None              # fp16 twin (16-bit storage path), built once
         self.data = data
         self.g = int(data.shape[0])
         self.ldx = int(data.shape[1])
         self.n = int(n)
         self.ncols = round_up(self.n, 4)
         assert self.ldx % 4 == 0 and self.ncols <= self.ldx
+
+    is_half = False
 
     @classmethod
     def from_host(cls, arr, kernels, device=None, band_bytes=256 << 20):
@@ -98,32 +100,33 @@ class DeviceMatrix:
             torch.cuda.current_stream().synchronize()
         return cls(out, n)
 
-    @property
-    def is_half(self):
-        return self.data.element_size() == 2
-
     def transposed(self, kernels, half=False):
-        """Resident transposed copy: cells x genes, leading dimension padded to 32 genes; fp32, or fp16 for the
-        16-bit storage path (always built from the fp32 matrix)."""
+        """Resident transposed copy (cells x genes): fp32 row-major with the leading dimension padded to 32 genes,
+        or -- 16-bit storage path -- the panel-major fp16 matrix."""
         torch = kernels.torch
+        if half:
+            out = torch.empty(kernels.panel_elems(max(self.n, 1), self.g), dtype=torch.float16, device=self.data.device)
+            if self.n > 0:
+                kernels.transpose_f16(self.data, self.ldx, self.g, self.n, out)
+            else:
+                out.zero_()
+            return HalfMatrix(out, max(self.n, 1), self.g, kernels.panel_rows(max(self.n, 1)))
         ldg = round_up(self.g, 32)
-        if self.is_half:
-            raise ValueError("the transposed copy is built from the fp32 matrix")
-        out = torch.zeros((max(self.n, 1), ldg), dtype=torch.float16 if half else torch.float32,
-                          device=self.data.device)
+        out = torch.zeros((max(self.n, 1), ldg), dtype=torch.float32, device=self.data.device)
         if self.n > 0:
-            (kernels.transpose_f16 if half else kernels.transpose)(self.data, self.ldx, self.g, self.n, out, ldg)
+            kernels.transpose(self.data, self.ldx, self.g, self.n, out, ldg)
         return DeviceMatrix(out, self.g, self.tf32_exact, self.f16_exact)
 
     def half_twin(self, kernels):
-        """fp16 storage of an fp16-exact fp32 matrix (same shape and leading dimension), built once and kept."""
-        if self.is_half:
-            return self
+        """Panel-major fp16 storage of an fp16-exact matrix, built once and kept."""
         if self._half is None:
             torch = kernels.torch
-            out = torch.empty((self.g, self.ldx), dtype=torch.float16, device=self.data.device)
-            kernels.narrow_f16(self.data, self.ldx, self.g, self.n, out, self.ldx)
-            self._half = DeviceMatrix(out, self.n, True, True)
+            out = torch.empty(kernels.panel_elems(self.g, max(self.n, 1)), dtype=torch.float16, device=self.data.device)
+            if self.n > 0:
+                kernels.narrow_f16(self.data, self.ldx, self.g, self.n, out)
+            else:
+                out.zero_()
+            self._half = HalfMatrix(out, self.g, self.n, kernels.panel_rows(self.g))
         return self._half
 
     def is_tf32_exact(self, kernels):
@@ -135,6 +138,28 @@ class DeviceMatrix:
         if self.f16_exact is None:
             self.f16_exact = bool(kernels.f16_exact(self.data))
         return self.f16_exact
+
+
+class HalfMatrix:
+    """fp16 storage of a (rows x cols) matrix in PANELS of 256 columns: element (i, j) at
+    ((j // 256) * rows_pad + i) * 256 + j % 256, rows_pad = rows rounded up to 64, padding zero
+    (include/scrna_b200.h, scrna_nmf_wtx_partial_h): the rows a sweep CTA streams are contiguous in HBM."""
+    is_half = True
+    PANEL = 256
+
+    def __init__(self, data, rows, cols, rows_pad):
+        self.data = data
+        self.g = int(rows)
+        self.n = int(cols)
+        self.rows_pad = int(rows_pad)
+        self.ldx = self.rows_pad          # what the C ABI takes in place of a leading dimension
+        self.ncols = round_up(self.n, 4)
+        self.npanels = (self.n + self.PANEL - 1) // self.PANEL
+
+    def dense(self):
+        """rows x cols view of the stored values (tests)."""
+        v = self.data.view(self.npanels, self.rows_pad, self.PANEL).permute(1, 0, 2)
+        return v.reshape(self.rows_pad, self.npanels * self.PANEL)[: self.g, : self.n]
 
 
 class TorchDistComm:
@@ -206,7 +231,7 @@ class NmfSolver:
 
         can_h = (bool(transpose_copy) and tensor_cores in ("auto", True, "f16")
                  and getattr(kernels, "h_supported", lambda kq: False)(round_up(self.k, 8)))
-        self.half = can_h and everywhere(X.is_half or X.is_f16_exact(kernels))
+        self.half = can_h and everywhere(X.is_f16_exact(kernels))
         if tensor_cores == "f16" and not self.half:
             raise ValueError("tensor_cores='f16' needs the transposed copy and an fp16-exact X")
         can_tc = (not self.half and bool(transpose_copy) and tensor_cores in ("auto", True, "tf32")
@@ -368,8 +393,8 @@ class NmfSolver:
         """K3: G^T . X over this shard -> split partials PB (SB x kp x ldn)."""
         kn, X, kp = self.kn, self.Xs, self.kp
         if self.half:
-            kn.wtx_partial_h(X.data, X.ldx, X.g, X.ncols, self.Gh, self.Ginv, kp, self.h_parts, self.PB, self.ldn,
-                             self.SB, ctrl)
+            kn.wtx_partial_h(X.data, X.rows_pad, X.g, X.ncols, self.Gh, self.Ginv, kp, self.h_parts, self.PB,
+                             self.ldn, self.SB, ctrl)
         elif self.tc:
             kn.wtx_partial_tc(X.data, X.ldx, X.g, X.ncols, self.Gtc, kp, self.PB, self.ldn, self.SB, ctrl,
                               flags=self.tc_flags)
@@ -380,8 +405,8 @@ class NmfSolver:
         """K1 on the transposed copy: (X . C^T)^T -> split partials PA (SA x kp x ldg)."""
         kn, XT, kp = self.kn, self.XT, self.kp
         if self.half:
-            kn.wtx_partial_h(XT.data, XT.ldx, XT.g, self.gcols, self.Ch, self.Cinv, kp, self.h_parts, self.PA, self.ldg,
-                             self.SA, ctrl)
+            kn.wtx_partial_h(XT.data, XT.rows_pad, XT.g, self.gcols, self.Ch, self.Cinv, kp, self.h_parts, self.PA,
+                             self.ldg, self.SA, ctrl)
         elif self.tc:
             kn.wtx_partial_tc(XT.data, XT.ldx, XT.g, self.gcols, self.Ctc, kp, self.PA, self.ldg, self.SA, ctrl,
                               flags=self.tc_flags)

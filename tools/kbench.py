@@ -105,7 +105,7 @@ def main():
             out.append(dict(kernel="xht_partial(lowmem K1)", k=k, nsplit=sa0, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
             print(out[-1], flush=True)
         Xr = slv.Xs.data
-        med, best = timeit(lambda: kn.residual(Xr, ldx, g, dm.ncols, slv.Gs32, slv.Ct32, slv.ldn, kp, 1, slv.res_part, slv.res_out))
+        med, best = timeit(lambda: kn.residual(Xr, slv.Xs.ldx, g, dm.ncols, slv.Gs32, slv.Ct32, slv.ldn, kp, 1, slv.res_part, slv.res_out))
         out.append(dict(kernel="residual_l1", k=k, ms=med, best_ms=best, gbs=bytes_x / med / 1e6))
         print(out[-1], flush=True)
         # whole iterations
