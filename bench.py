@@ -41,9 +41,10 @@ def ncu_traffic(path):
         return None
 
 UNIT = "iterations/s"
+WORKLOAD = "NMF MU %d genes x %d cells k=%d, cells sharded over the GPUs (BASELINE.json configs[2])"
 E2E_ITERS = 100                        # NmfClustering.apply default max_iter (nmf_clustering.py:20)
-CPU_SAMPLE_CELLS = 10000
-CPU_SAMPLE_ITERS = 4
+CPU_SAMPLE_CELLS = 25000             # in-run cpu_baseline leg of the GPU arm: a quarter of the cells, ~10-20 s
+CPU_SAMPLE_ITERS = 3
 
 
 def measured_peaks():
@@ -141,126 +142,298 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU legs (the only place bench.py executes oracle/): the reference's arithmetic on the host cores
+# CPU legs (the only place bench.py executes oracle/): the reference's arithmetic on the host cores.
+# The MU solver the metric names is scikit-learn's own `_fit_multiplicative_update` (the reference delegates its
+# arithmetic to sklearn); the reference's STOCK solver is `decomp.NMF(solver='cd')` as
+# scRNA/nmf_clustering.py:25-29 constructs it, run through the unmodified reference package installed by
+# oracle/make_ref.py into oracle/_ref under the compatibility shim oracle/refshim.py.
 # ---------------------------------------------------------------------------------------------
-def cpu_mu_iterations(X64, W0, H0, iters):
-    """Times `iters` iterations of the oracle's sklearn-MU restatement (numpy/BLAS, all host threads:
-    torchrun exports OMP_NUM_THREADS=1 to its workers, so the BLAS pools are widened explicitly)."""
-    from oracle import nmf_oracle as no
+def _all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: widen the BLAS pools explicitly."""
     try:
         from threadpoolctl import threadpool_limits
-        limiter = threadpool_limits(limits=os.cpu_count() or 1)
+        return threadpool_limits(limits=os.cpu_count() or 1)
     except Exception:
-        limiter = None
-    W, H = W0.copy(), H0.copy()
-    t0 = time.perf_counter()
-    for _ in range(iters):
-        W = no.mu_update_w(X64, W, H, L1, L2)
-        H = no.mu_update_h(X64, W, H, L1, L2)
-    dt = (time.perf_counter() - t0) / iters
+        return None
+
+
+def sklearn_mu_seconds_per_iteration(X64, W0, H0, iters):
+    """Seconds per iteration of sklearn's `_fit_multiplicative_update` (fp64, all host threads): the difference
+    of a (1 + iters)-iteration and a 1-iteration call, so that the one-off initial error evaluation drops out.
+    tol = 0: exactly max_iter iterations, no convergence checks (SP/sklearn/decomposition/_nmf.py:866)."""
+    from sklearn.decomposition._nmf import _fit_multiplicative_update
+    limiter = _all_host_threads()
+
+    def call(n):
+        W, H = W0.copy(), H0.copy()
+        t0 = time.perf_counter()
+        _fit_multiplicative_update(X64, W, H, "frobenius", n, 0.0, L1, L1, L2, L2, True, 0)
+        return time.perf_counter() - t0
+
+    call(1)                      # untimed: BLAS thread pools, first-touch page faults of the temporaries
+    t1 = call(1)
+    tn = call(1 + iters)
     if limiter is not None:
         limiter.restore_original_limits()
-    return dt
+    if tn <= t1:                 # timer noise on a tiny sample: fall back to the whole call
+        return tn / (1 + iters), t1
+    return (tn - t1) / iters, t1
 
 
-def cpu_sample(sample_cells, seed=1234):
-    """Host fp64 sample of the workload: genes x sample_cells (drawn on the GPU when there is one --
-    data generation is not part of any timed region -- else with the numpy twin of the generator)."""
+def reference_cd_seconds_per_iteration(X64, W0, H0, iters):
+    """Seconds per iteration of the reference's stock solver: the `decomp.NMF(alpha=, init=, l1_ratio=, max_iter=,
+    n_components=, random_state=0, shuffle=True, solver='cd', tol=)` object scRNA/nmf_clustering.py:25-29 builds
+    (era `alpha` semantics via oracle/refshim.py item 3), started from the given factors so that the timing
+    is the iteration loop and not the NNDSVDar init."""
+    from oracle import refshim
+    refshim.install()
+    from sklearn import decomposition as decomp
+    import warnings
+    limiter = _all_host_threads()
+
+    def call(n):
+        m = decomp.NMF(alpha=10., init="custom", l1_ratio=0.75, max_iter=n, n_components=W0.shape[1], random_state=0,
+                       shuffle=True, solver="cd", tol=0.0, verbose=0)
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m.fit_transform(X64, W=W0.copy(), H=H0.copy())
+        return time.perf_counter() - t0
+
+    call(1)
+    t1 = call(1)
+    tn = call(1 + iters)
+    if limiter is not None:
+        limiter.restore_original_limits()
+    return (tn - t1) / iters if tn > t1 else tn / (1 + iters)
+
+
+def host_counts(genes, cell_begin, cell_end, seed=1234):
+    """Host fp64 copy of cells [cell_begin, cell_end) of the workload (drawn on the GPU when there is one -- data
+    generation is not part of any timed region -- else with the numpy twin of the generator)."""
+    n = cell_end - cell_begin
     try:
         import torch
         if torch.cuda.is_available():
-            Xd, n = synth_counts(torch, torch.device("cuda", torch.cuda.current_device()), GENES, 0, sample_cells,
-                                 seed=seed)
-            out = Xd[:, :n].to(torch.float64).cpu().numpy()
-            del Xd
+            dev = torch.device("cuda", torch.cuda.current_device())
+            out = np.empty((genes, n), dtype=np.float64)
+            for b0 in range(cell_begin, cell_end, CELL_BLOCK):      # block by block: bounded device memory
+                b1 = min(cell_end, b0 + CELL_BLOCK)
+                Xd, nb = synth_counts(torch, dev, genes, b0, b1, seed=seed)
+                out[:, b0 - cell_begin: b1 - cell_begin] = Xd[:, :nb].to(torch.float64).cpu().numpy()
+                del Xd
             torch.cuda.empty_cache()
             return out
     except Exception:
         pass
     rng = np.random.RandomState(seed)
-    mean = rng.gamma(2.0, 0.5, size=(GENES, 1)) * (0.5 + rng.rand(GENES, 1))
-    de = rng.rand(GENES, 8) < (0.1 + 0.3 * rng.rand(1, 8))
-    lfc = (1.0 + 0.5 * rng.randn(GENES, 8)) * np.where(rng.rand(GENES, 8) < 0.5, -1.0, 1.0)
+    mean = rng.gamma(2.0, 0.5, size=(genes, 1)) * (0.5 + rng.rand(genes, 1))
+    de = rng.rand(genes, 8) < (0.1 + 0.3 * rng.rand(1, 8))
+    lfc = (1.0 + 0.5 * rng.randn(genes, 8)) * np.where(rng.rand(genes, 8) < 0.5, -1.0, 1.0)
     fold = np.where(de, 2.0 ** lfc, 1.0)
-    label = rng.randint(0, 8, size=sample_cells)
-    size = 2.0 ** (0.5 * rng.randn(sample_cells))
-    X = np.empty((GENES, sample_cells))
-    for r0 in range(0, GENES, 2000):
+    label = rng.randint(0, 8, size=n)
+    size = 2.0 ** (0.5 * rng.randn(n))
+    X = np.empty((genes, n))
+    for r0 in range(0, genes, 2000):
         mu = mean[r0:r0 + 2000] * fold[r0:r0 + 2000][:, label] * size[None, :]
         X[r0:r0 + 2000] = rng.poisson(rng.gamma(10.0, mu / 10.0))
     return X
 
 
-def sc3_consensus_seconds(cells, genes, k=8):
-    """Second half of BASELINE.json's metric ("SC3 consensus s"): the reference CLI's default SC3 configuration
-    (euclidean distances, pca transformation, <= 15 sampled dimensions in [0.04 n, 0.07 n], KMeans n_init=10,
-    consensus matrix, complete linkage; sc3_clustering.py:58-109) on a synthetic target of `cells` cells, device
-    seconds per stage.  The 20 000-cell configuration takes minutes and is recorded under profiles/."""
-    import torch
-    from scrna_b200.sc3_device import Sc3Ops, kmeans_draw_count
-    ops = Sc3Ops()
-    rng = np.random.RandomState(cells)
-    centers = rng.gamma(2.0, 2.0, size=(genes, k))
-    lab = rng.randint(0, k, size=cells)
-    X = rng.poisson(centers[:, lab] * 2.0 ** (0.3 * rng.randn(1, cells))).astype(np.float64)
-    Xd = ops.to_device(X)
-    ops.distances(X[:, :64], "euclidean")  # warm-up
-    stages = {}
+def host_ram_available():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 0
 
-    def timed(name, fn):
-        torch.cuda.synchronize()
+
+def small_data_leg():
+    """BASELINE.json configs[0]/[1] on the default simulated data (tests/golden/default_sim.npz: 1000 genes, 1000
+    source / 100 target cells): source dictionary (NmfClustering_initW, CLI parameters) -> target transfer + mixed
+    data (DaNmfClustering.get_mixed_data, mix = .5) -> SC3 consensus clustering (cmd_target.py:220-242 wiring), once
+    through scrna_b200 and once through the UNMODIFIED reference classes (oracle/_ref under oracle/refshim.py) on
+    the host cores, wall clock, same seeds; the final labels must be identical."""
+    from functools import partial
+    d = np.load(os.path.join(ROOT, "tests", "golden", "default_sim.npz"))
+    src, trg = d["src"].astype(np.float64), d["trg"].astype(np.float64)
+    src_labels, gene_ids, k = d["src_labels"], np.arange(src.shape[0]), 7
+    n = trg.shape[1]
+    pc = [max(1, int(np.floor(0.04 * n))), int(np.ceil(0.07 * n))]
+
+    def flow(nmf_mod, sc3_mod, sc):
+        t = {}
         t0 = time.perf_counter()
-        out = fn()
-        torch.cuda.synchronize()
-        stages[name] = time.perf_counter() - t0
+        s = nmf_mod.NmfClustering_initW(src, gene_ids, k, src_labels)
+        s.apply(k=k, alpha=10., l1=0.75, max_iter=4000, rel_err=1e-3)
+        t["source_nmf_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        np.random.seed(1)
+        da = nmf_mod.DaNmfClustering(s, trg.copy(), gene_ids, k)
+        mixed, _, _ = da.get_mixed_data(mix=0.5)
+        t["target_transfer_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        np.random.seed(3)
+        s3 = sc3_mod.SC3Clustering(mixed, gene_ids, pc_range=pc, sub_sample=True, consensus_mode=0)
+        s3.add_distance_calculation(partial(sc.distances, metric="euclidean"))
+        s3.add_dimred_calculation(partial(sc.transformations, components=pc[1], method="pca"))
+        s3.add_intermediate_clustering(partial(sc.intermediate_kmeans_clustering, k=k))
+        s3.set_build_consensus_matrix(sc.build_consensus_matrix)
+        s3.set_consensus_clustering(partial(sc.consensus_clustering, n_components=k))
+        s3.apply()
+        t["sc3_s"] = time.perf_counter() - t0
+        t["total_s"] = sum(t.values())
+        return t, np.asarray(s.cluster_labels), np.asarray(da.cluster_labels), np.asarray(s3.cluster_labels)
+
+    import scrna_b200
+    from scrna_b200 import sc3_clustering_impl as our_sc
+    flow(scrna_b200, scrna_b200, our_sc)                       # warm-up: library load, kernel attributes
+    ours = flow(scrna_b200, scrna_b200, our_sc)
+    out = {"config": "default simulated data (1000 genes, 1000 source / 100 target cells, k=7): NmfClustering_initW "
+                     "-> DaNmfClustering.get_mixed_data(mix=.5) -> SC3Clustering (euclidean, pca, n_init=10)",
+           "b200": ours[0]}
+    try:
+        from oracle import refshim
+        ref = refshim.import_reference()
+        limiter = _all_host_threads()
+        theirs = flow(ref.nmf_clustering, ref.sc3_clustering, ref.sc3_clustering_impl)
+        if limiter is not None:
+            limiter.restore_original_limits()
+        out["reference"] = theirs[0]
+        out["reference_kind"] = "unmodified reference classes from %s on %d host cores" % (
+            os.path.relpath(refshim.REFERENCE_ROOT, ROOT) if refshim.REFERENCE_ROOT.startswith(ROOT)
+            else refshim.REFERENCE_ROOT, os.cpu_count() or 1)
+        out["labels_equal"] = {"source": bool(np.array_equal(ours[1], theirs[1])),
+                               "target_transfer": bool(np.array_equal(ours[2], theirs[2])),
+                               "sc3": bool(np.array_equal(ours[3], theirs[3]))}
+        out["speedup_total"] = theirs[0]["total_s"] / ours[0]["total_s"]
+    except Exception as e:  # the reference package is test infrastructure: its absence must not sink the bench
+        out["reference"] = None
+        out["reference_error"] = "%s: %s" % (type(e).__name__, e)
+    return out
+
+
+def sc3_consensus_seconds(cells, genes, k=8):
+    """Second half of BASELINE.json's metric ("SC3 consensus s", configs[3]): the reference CLI's default SC3
+    configuration (euclidean distances, pca transformation, 15 sampled dimensions in [0.04 n, 0.07 n], KMeans
+    n_init=10, consensus matrix, complete linkage; cmd_target.py:220-242 wiring of sc3_clustering.py:58-109) on a
+    synthetic target of `cells` cells, wall seconds of `SC3Clustering.apply()` through the class API (NumPy in,
+    NumPy out at every plug-in boundary), with per-stage device seconds and the FP64-pipe fraction of the dense
+    stages."""
+    import torch
+    from functools import partial
+    from scrna_b200 import SC3Clustering
+    from scrna_b200 import sc3_clustering_impl as sc
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(cells)
+    centers = torch._standard_gamma(torch.full((genes, k), 2.0, device=dev), generator=gen) * 2.0
+    lab = torch.randint(0, k, (cells,), device=dev, generator=gen)
+    size = torch.pow(2.0, 0.3 * torch.randn(cells, device=dev, generator=gen))
+    X = np.empty((genes, cells), dtype=np.float64)
+    for r0 in range(0, genes, 2000):
+        r1 = min(genes, r0 + 2000)
+        X[r0:r1] = torch.poisson(centers[r0:r1][:, lab] * size[None, :], generator=gen).double().cpu().numpy()
+    lab = lab.cpu().numpy()
+    del centers, size
+    torch.cuda.empty_cache()
+    ops = sc._ops()
+    ops.distances(X[:, :64], "euclidean")  # warm-up
+    ops.stage_seconds = {}
+    np.random.seed(0)
+    pc = [max(1, int(np.floor(0.04 * cells))), int(np.ceil(0.07 * cells))]
+    s3 = SC3Clustering(X, np.arange(genes), pc_range=pc, sub_sample=True, consensus_mode=0)
+    kept = {}
+
+    def dimred(D):
+        out = sc.transformations(D, components=pc[1], method="pca")
+        kept["vecs"] = out[1]
         return out
 
-    D = timed("distances_euclidean", lambda: ops.distances(Xd, "euclidean"))
-    pc = [max(1, int(np.floor(0.04 * cells))), int(np.ceil(0.07 * cells))]
-    V, _ = timed("pca_right_singular_vectors", lambda: ops.right_singular_vectors(ops.transform_matrix(D, "pca"), pc[1]))
-    dims = list(range(pc[0], pc[1] + 1))
-    if len(dims) > 15:
-        dims = list(np.random.RandomState(0).permutation(dims)[:15])
-    per, _ = kmeans_draw_count(k)
-    draws = [np.random.RandomState(int(d)).random_sample(10 * per) for d in dims]
-    labs = timed("kmeans_ensemble", lambda: [ops.kmeans(V, int(d), k, u) for d, u in zip(dims, draws)])
-
-    def cons():
-        M = ops.coassoc_new(cells)
-        for l in labs:
-            ops.coassoc_add(M, l)
-        return ops.consensus_clustering(ops.consensus_from_counts(M, float(len(labs))), k)
-    timed("consensus_and_linkage", cons)
-    return {"cells": cells, "genes": genes, "k": k, "seconds": sum(stages.values()), "stages": stages,
-            "jacobi_sweeps": ops.jacobi_sweeps, "dims": len(dims),
-            "config": "1 distance (euclidean) x 1 transformation (pca), n_init=10: cmd_target.py defaults",
-            "at_20000_cells": "profiles/r01_sc3_20k_cells_stage_seconds.json"}
+    s3.add_distance_calculation(partial(sc.distances, metric="euclidean"))
+    s3.add_dimred_calculation(dimred)
+    s3.add_intermediate_clustering(partial(sc.intermediate_kmeans_clustering, k=k))
+    s3.set_build_consensus_matrix(sc.build_consensus_matrix)
+    s3.set_consensus_clustering(partial(sc.consensus_clustering, n_components=k))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s3.apply()
+    torch.cuda.synchronize()
+    seconds = time.perf_counter() - t0
+    stages = dict(ops.stage_seconds)
+    ops.stage_seconds = None
+    from sklearn.metrics import adjusted_rand_score
+    # diagnostic, outside the timed region: one k-means on the k leading vectors only.  The cluster structure lives
+    # in the first k - 1 directions; SC3's rule (sc3_clustering.py:82-85 with cmd_target.py:220-238) instead
+    # clusters on d in [0.04 n, 0.07 n] = 800..1400 dimensions at this size, nearly all of them noise, which is what
+    # pulls the consensus ARI down as n grows (profiles/r02_sc3_ari_vs_cells.json) -- the vectors themselves are fine.
+    lead = np.ascontiguousarray(kept["vecs"][:, :k])
+    ari_lead = float(adjusted_rand_score(lab, np.asarray(sc.intermediate_kmeans_clustering(lead, k=k)).ravel()))
+    fp64_peak = 37.0e12          # B200 FP64 (DFMA or DMMA) flop/s: 18.5 TFMA/s measured, profiles/r01_dmma_rate_microbench.txt
+    n = float(cells)
+    flops = {"distances": 3.0 * n * n * genes / 2.0,          # sub, fma per gene over the upper triangle
+             "svd": None, "consensus_row_distances": 3.0 * n * n * n / 2.0}
+    frac = {}
+    for name in ("distances", "consensus_row_distances"):
+        if stages.get(name):
+            frac[name] = flops[name] / stages[name] / fp64_peak
+    if stages.get("svd") and getattr(ops, "svd_flops", None):
+        frac["svd"] = ops.svd_flops / stages["svd"] / fp64_peak
+    return {"cells": cells, "genes": genes, "k": k, "seconds": seconds, "stages": stages,
+            "fp64_pipe_fraction": frac, "fp64_peak_flops": fp64_peak,
+            "jacobi_sweeps": ops.jacobi_sweeps, "dims": 15 if pc[1] - pc[0] + 1 > 15 else pc[1] - pc[0] + 1,
+            "ari_vs_simulated_labels": float(adjusted_rand_score(lab, s3.cluster_labels)),
+            "ari_kmeans_on_leading_k_vectors_only": ari_lead,
+            "through": "SC3Clustering.apply() (class API, NumPy at every plug-in boundary)",
+            "config": "1 distance (euclidean) x 1 transformation (pca), n_init=10: cmd_target.py defaults "
+                      "(BASELINE.json configs[3])"}
 
 
 def run_reference(args):
+    """The reference arm: the SAME configuration as the GPU arm (20 000 genes x 100 000 cells, k = 8, alpha 10,
+    l1_ratio .75), fp64, on the host cores.  value = sklearn's own MU iteration rate over the full matrix;
+    `stock_cd` = the reference's stock coordinate-descent solver on the same matrix."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    genes, cells, k = args.genes, args.cells, args.k
     cores = os.cpu_count() or 1
-    X = cpu_sample(CPU_SAMPLE_CELLS)
+    need = genes * cells * 8 * 3.5            # X + the two temporaries of sklearn's initial error evaluation
+    ram = host_ram_available()
+    same_config = ram == 0 or ram > need
+    sample_cells = cells if same_config else max(1000, int(cells * 0.25 * ram / need) // 1000 * 1000)
+    X = host_counts(genes, 0, sample_cells)
     rng = np.random.RandomState(0)
-    W0, H0 = init_factors(rng, GENES, CPU_SAMPLE_CELLS, K, X.mean())
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_mu_iterations(X, W0, H0, 1)
+    W0, H0_full = init_factors(rng, genes, cells, k, X.mean())
+    H0 = np.ascontiguousarray(H0_full[:, :sample_cells])
     steps = max(1, args.steps)
-    sec = cpu_mu_iterations(X, W0, H0, steps)
-    scale = CPU_SAMPLE_CELLS / float(CELLS)
+    sec, first_call = sklearn_mu_seconds_per_iteration(X, W0, H0, steps)
+    cd_iters = max(1, min(3, steps))
+    try:
+        sec_cd = reference_cd_seconds_per_iteration(X, W0, H0, cd_iters)
+        cd = {"value": (sample_cells / float(cells)) / sec_cd, "unit": UNIT, "iterations_timed": cd_iters,
+              "what": "decomp.NMF(alpha=10, init='custom', l1_ratio=.75, n_components=%d, random_state=0, shuffle=True, "
+                      "solver='cd', tol=0) as scRNA/nmf_clustering.py:25-29 builds it (era alpha semantics, "
+                      "oracle/refshim.py), from the same start factors" % k}
+    except Exception as e:
+        cd = {"value": None, "error": "%s: %s" % (type(e).__name__, e)}
+    scale = sample_cells / float(cells)
     value = scale / sec
-    sample = ("%d MU iterations (oracle restatement of sklearn _fit_multiplicative_update, fp64, numpy/BLAS) on "
-              "%d genes x %d cells = 1/%d of the cells; per-iteration time scaled linearly in cells to %d"
-              % (steps, GENES, CPU_SAMPLE_CELLS, int(round(1 / scale)), CELLS))
+    sample = ("%d iterations of sklearn.decomposition._nmf._fit_multiplicative_update (fp64, tol=0, all %d host "
+              "threads) on the full %d genes x %d cells matrix (%.1f GB), timed as the difference of a %d- and a "
+              "1-iteration call" % (steps, cores, genes, sample_cells, genes * sample_cells * 8 / 1e9, steps + 1))
+    if not same_config:
+        sample += "; host RAM (%.0f GB available) does not hold the full matrix: %d of %d cells, scaled linearly" % (
+            ram / 1e9, sample_cells, cells)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": args.warmup, "ms_per_step": sec / scale * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "NMF MU 20000 genes x 100000 cells k=8 (CPU leg on a bounded sample)",
-                   "genes": GENES, "cells": CELLS, "k": K, "l1": L1, "l2": L2, "solver": "mu"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC if k == K else METRIC.replace("k=8", "k=%d" % k), "value": value,
+        "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": sec / scale * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD % (genes, cells, k), "genes": genes, "cells": cells, "k": k, "l1": L1, "l2": L2,
+                   "solver": "mu", "same_config": same_config, "host_ram_available_gb": ram / 1e9},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+                         "first_call_seconds": first_call},
+        "stock_cd": cd,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -444,15 +617,21 @@ def run_gpu(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        Xs = cpu_sample(CPU_SAMPLE_CELLS)
-        Ws, Hs = init_factors(np.random.RandomState(0), genes, CPU_SAMPLE_CELLS, k, Xs.mean())
-        cpu_mu_iterations(Xs, Ws, Hs, 1)
-        sec = cpu_mu_iterations(Xs, Ws, Hs, CPU_SAMPLE_ITERS)
-        scale = CPU_SAMPLE_CELLS / float(cells)
-        cpu_baseline = {"value": scale / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "%d MU iterations of the oracle (sklearn _fit_multiplicative_update restated, fp64, "
-                                  "numpy/BLAS on all host threads) on %d genes x %d cells; scaled linearly in cells to %d"
-                                  % (CPU_SAMPLE_ITERS, genes, CPU_SAMPLE_CELLS, cells)}
+        sc_cells = min(cells, CPU_SAMPLE_CELLS)
+        Xs = host_counts(genes, 0, sc_cells)
+        Ws, Hs = init_factors(np.random.RandomState(0), genes, sc_cells, k, Xs.mean())
+        sec, _ = sklearn_mu_seconds_per_iteration(Xs, Ws, Hs, CPU_SAMPLE_ITERS)
+        del Xs
+        scale = sc_cells / float(cells)
+        cpu_baseline = {"value": scale / sec, "unit": UNIT, "cores": cores, "kind": "reference",
+                        "sample": "%d iterations of sklearn's own _fit_multiplicative_update (fp64, all host threads) on "
+                                  "%d genes x %d cells = 1/%d of the cells, scaled linearly in cells; the full-size, "
+                                  "same-config run is `bench.py --impl reference`"
+                                  % (CPU_SAMPLE_ITERS, genes, sc_cells, int(round(1 / scale)))}
+
+    small = None
+    if rank == 0 and world == 1 and not args.no_small:
+        small = small_data_leg()
 
     sc3 = None
     if rank == 0 and world == 1 and args.sc3_cells > 0:
@@ -463,8 +642,7 @@ def run_gpu(args):
             "metric": METRIC if k == K else METRIC.replace("k=8", "k=%d" % k), "value": value, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "NMF MU %d genes x %d cells k=%d, cells sharded over the GPUs "
-                                   "(BASELINE.json configs[2])" % (genes, cells, k),
+            "config": {"workload": WORKLOAD % (genes, cells, k),
                        "genes": genes, "cells": cells, "k": k, "solver": "mu", "l1": L1, "l2": L2,
                        "x_storage": ("fp16 (every count exactly representable) genes x cells + resident transposed copy"
                                      if slv_half else "fp32 genes x cells + resident transposed copy"),
@@ -479,7 +657,7 @@ def run_gpu(args):
             "launch": {"mode": "cuda graph replay (one graph per iteration)" if (ms_graph is not None and ms == ms_graph)
                        else "eager launches", "eager_ms_per_step": ms_eager / args.steps,
                        "graph_ms_per_step": None if ms_graph is None else ms_graph / args.steps},
-            "cpu_baseline": cpu_baseline, "sc3_consensus": sc3,
+            "cpu_baseline": cpu_baseline, "sc3_consensus": sc3, "small_data": small,
         }
         emit(line)
     shutdown_distributed(world)
@@ -549,8 +727,10 @@ def main():
     ap.add_argument("--graph", type=int, default=-1,
                     help="0: eager launches only; otherwise (default) the K steps are timed a second time as CUDA-graph "
                          "replays (kernels + NCCL all-reduce) and the faster of the two is reported")
-    ap.add_argument("--sc3-cells", type=int, default=4000,
-                    help="cells (= genes) of the SC3 consensus timing appended at N=1; 0 skips it")
+    ap.add_argument("--sc3-cells", type=int, default=20000,
+                    help="cells (= genes) of the SC3 consensus timing appended at N=1 (BASELINE.json configs[3]: 20000); "
+                         "0 skips it")
+    ap.add_argument("--no-small", action="store_true", help="skip the configs[0]/[1] small-data leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: stop after the device-timed region")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per sweep launch from the committed ncu capture (profiles/)")

@@ -47,6 +47,11 @@ _resident = {}
 
 
 def _remember(host_array, device_tensor):
+    """Pair a stage's host result with its device twin.  The host array is made READ-ONLY: the twin is found again
+    by the array's identity, so an in-place edit between two stages (`D /= D.max()`, `D[np.isnan(D)] = 0`, ...)
+    would otherwise make the next stage run silently on the stale device copy.  Such an edit now raises
+    `ValueError: assignment destination is read-only`; edit a copy instead (a copy has no twin and is uploaded)."""
+    host_array.flags.writeable = False
     key = id(host_array)
     _resident[key] = (weakref.ref(host_array, lambda _r, k=key: _resident.pop(k, None)), device_tensor)
     return host_array

@@ -5,6 +5,9 @@ Every array operation is a C-ABI kernel (include/scrna_b200.h); the host sequenc
 few scalars per k-means iteration / Jacobi sweep for the stop rules, and draws nothing: random inputs
 (k-means++ uniforms) are passed in, pre-drawn from the reference's RNG stream.
 """
+import contextlib
+import time
+
 import numpy as np
 
 from . import _lib
@@ -36,6 +39,24 @@ class Sc3Ops:
         self.kn = kernels
         self.torch = kernels.torch
         self.dev = self.torch.device("cuda", self.torch.cuda.current_device())
+        self.stage_seconds = None   # bench.py sets a dict: synchronised wall seconds accumulated per stage
+        self.svd_flops = 0.0
+        self.jacobi_sweeps = 0
+        self._last = None
+
+    @contextlib.contextmanager
+    def _stage(self, name):
+        ss = self.stage_seconds
+        if ss is None:
+            yield
+            return
+        self.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        try:
+            yield
+        finally:
+            self.torch.cuda.synchronize()
+            ss[name] = ss.get(name, 0.0) + time.perf_counter() - t0
 
     # ---- plumbing ---------------------------------------------------------------------------------
     def _s(self):
@@ -76,7 +97,12 @@ class Sc3Ops:
 
     def distances(self, X, metric="euclidean", comm=None):
         """X: genes x cells (numpy or device fp64) -> device n x n distance matrix."""
-        Xd = self.to_device(X)
+        with self._stage("upload"):
+            Xd = self.to_device(X)
+        with self._stage("distances"):
+            return self._distances(Xd, metric, comm)
+
+    def _distances(self, Xd, metric, comm):
         F, N = Xd.shape
         out = self.empty(N, N)
         if metric == "euclidean":
@@ -100,6 +126,10 @@ class Sc3Ops:
 
     # ---- a13 transformations ------------------------------------------------------------------------
     def transform_matrix(self, D, method="pca"):
+        with self._stage("transform"):
+            return self._transform_matrix(D, method)
+
+    def _transform_matrix(self, D, method):
         D = self.to_device(D)
         n = D.shape[0]
         out = self.empty(n, n)
@@ -125,7 +155,8 @@ class Sc3Ops:
         if blocked is None:
             blocked = n > 64
         if blocked:
-            return self._rsv_blocked(M, components, max_sweeps, tol)
+            with self._stage("svd"):
+                return self._rsv_blocked(M, components, max_sweeps, tol)
         AT = self.empty(n, n)
         VT = self.empty(n, n)
         self._call("scrna_jacobi_init_f64", M, n, n, AT, VT, n, self._s(), launches=2)
@@ -170,6 +201,8 @@ class Sc3Ops:
             self.jacobi_sweeps += 1
             if int(rotated.cpu()[0]) == 0:
                 break
+        nb = n_pad // 32
+        self.svd_flops = self.jacobi_sweeps * (nb * (nb - 1) / 2.0) * (2 * 64 * 64 * n) * 2.0   # Gram + apply, 2 flop/FMA
         sq = self.empty(n)
         self._call("scrna_row_sqnorm_f64", W, n, n, sq, self._s())
         vals = np.sqrt(np.maximum(sq.cpu().numpy(), 0.0))
@@ -203,6 +236,10 @@ class Sc3Ops:
     def kmeans(self, V, d, k, draws, n_init=10, max_iter=10000):
         """KMeans(n_clusters=k, n_init, max_iter, init='k-means++').fit_predict(V[:, :d]); `draws` are the
         n_init * kmeans_draw_count(k) uniforms of the reference's RNG stream.  Returns int32 device labels."""
+        with self._stage("kmeans_ensemble"):
+            return self._kmeans(V, d, k, draws, n_init, max_iter)
+
+    def _kmeans(self, V, d, k, draws, n_init, max_iter):
         t = self.torch
         V = self.to_device(V)
         n, ldv = V.shape[0], V.stride(0)
@@ -276,7 +313,8 @@ class Sc3Ops:
         n = M.shape[0]
         if not isinstance(labels, t.Tensor):
             labels = t.from_numpy(np.ascontiguousarray(labels, dtype=np.int32)).to(self.dev)
-        self._call("scrna_coassoc_accum", labels, n, M, n, self._s())
+        with self._stage("coassociation"):
+            self._call("scrna_coassoc_accum", labels, n, M, n, self._s())
 
     def consensus_from_counts(self, M, cnt):
         n = M.shape[0]
@@ -291,7 +329,13 @@ class Sc3Ops:
         C = self.to_device(C)
         n = C.shape[0]
         D = self.empty(n, n)
-        self._call("scrna_pairwise_f64", C, n, n, n, 0, D, n, self._s())
+        with self._stage("consensus_row_distances"):
+            self._call("scrna_pairwise_f64", C, n, n, n, 0, D, n, self._s())
+        with self._stage("linkage"):
+            return self._linkage(D, n, n_clusters)
+
+    def _linkage(self, D, n, n_clusters):
+        t = self.torch
         Dwork = D.clone()
         labels = self.zeros(n, dtype=t.int32)
         Z = self.zeros(max(n - 1, 1), 4)
