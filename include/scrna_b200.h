@@ -352,6 +352,9 @@ int scrna_hclust_complete(double* D, int64_t ld, int n, int n_clusters, int32_t*
  * the reference uses dense n^3 products).  partials: 3 * scrna_kta_blocks() doubles. */
 int scrna_kta_blocks(void);
 int scrna_kta_rowstats_f64(const double* K, int64_t ld, int n, double* rowsum, double* diag, void* stream);
+/* Gaussian kernel from the linear Gram, in place: K_ij <- exp(-(diag_i - 2 K_ij + diag_j) / param), diag = the Gram's
+ * diagonal copied beforehand (get_kernel(type='rbf'), scRNA/utils.py:108-124; unsupervised_acc_kta(kernel='rbf')). */
+int scrna_kta_rbf_f64(double* K, int64_t ld, int n, const double* diag, double param, void* stream);
 int scrna_kta_align_f64(const double* K, int64_t ld, int n, const int32_t* labels, const double* mean_x,
                         const double* scale_x, double tot_x, const double* mean_y, const double* scale_y, double tot_y,
                         double* partials, double* out, void* stream);

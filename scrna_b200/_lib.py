@@ -95,6 +95,7 @@ _SIGNATURES = {
     "scrna_gather_rows_scaled_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr],
     "scrna_kta_blocks": [],
     "scrna_kta_rowstats_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr],
+    "scrna_kta_rbf_f64": [c_ptr, c_i64, c_int, c_ptr, c_dbl, c_ptr],
     "scrna_kta_align_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr],
     "scrna_km_prepare": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_kmeans_pp": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_dbl, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,

@@ -56,6 +56,18 @@ kta_align_kernel(const double* __restrict__ K, int64_t ld, int n, const int* __r
   }
 }
 
+// Gaussian kernel from the linear Gram, in place: K_ij <- exp(-(K_ii - 2 K_ij + K_jj) / param)  (get_kernel(type='rbf'),
+// scRNA/utils.py:108-124).  The diagonal is read from a copy taken before the pass.
+__global__ void __launch_bounds__(256)
+kta_rbf_kernel(double* __restrict__ K, int64_t ld, int n, const double* __restrict__ diag, double param) {
+  const int i = blockIdx.y;
+  const double di = diag[i];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const double v = di - 2.0 * K[(int64_t)i * ld + j] + diag[j];
+    K[(int64_t)i * ld + j] = exp(-v / param);
+  }
+}
+
 __global__ void kta_final_kernel(const double* __restrict__ partials, int nblk, double* __restrict__ out) {
   if (threadIdx.x < 3) {
     double s = 0.0;
@@ -73,6 +85,13 @@ extern "C" int scrna_kta_blocks(void) { return 4 * num_sms(); }
 extern "C" int scrna_kta_rowstats_f64(const double* K, int64_t ld, int n, double* rowsum, double* diag, void* stream) {
   if (!K || !rowsum || !diag || n <= 0 || ld < n) return SCRNA_ERR_BADARG;
   kta_rowstats_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(K, ld, n, rowsum, diag);
+  return last_launch_status();
+}
+
+extern "C" int scrna_kta_rbf_f64(double* K, int64_t ld, int n, const double* diag, double param, void* stream) {
+  if (!K || !diag || n <= 0 || ld < n || n > 65535 || !(param != 0.0)) return SCRNA_ERR_BADARG;
+  dim3 grid((unsigned)(ceil_div(n, 256) > 32 ? 32 : ceil_div(n, 256)), (unsigned)n);
+  kta_rbf_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(K, ld, n, diag, param);
   return last_launch_status();
 }
 

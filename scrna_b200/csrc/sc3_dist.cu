@@ -128,25 +128,33 @@ __global__ void corr_epilogue_kernel(const double* __restrict__ G, int64_t ldg, 
 }
 
 // K10: average ranks (1-based) of each ROW of Xt (N cells x F genes, row-major): one CTA per cell,
-// the cell's vector staged in shared memory, rank_i = #{x < x_i} + (#{x == x_i} + 1) / 2.
+// rank_i = #{x < x_i} + (#{x == x_i} + 1) / 2.  The cell's vector is staged in shared memory in chunks of `chunk`
+// genes (one chunk for up to 27 648 genes); the counts against successive chunks are accumulated in the output
+// row itself -- half-integers, exact in fp64 -- so the gene count is not limited by shared memory.
 __global__ void __launch_bounds__(1024)
-rank_avg_kernel(const double* __restrict__ Xt, int64_t ld, int N, int F, double* __restrict__ R,
+rank_avg_kernel(const double* __restrict__ Xt, int64_t ld, int N, int F, int chunk, double* __restrict__ R,
                 int64_t ldr) {
   extern __shared__ double sv[];
   const int cell = blockIdx.x;
   if (cell >= N) return;
   const double* row = Xt + (int64_t)cell * ld;
-  for (int f = threadIdx.x; f < F; f += blockDim.x) sv[f] = row[f];
-  __syncthreads();
-  for (int f = threadIdx.x; f < F; f += blockDim.x) {
-    const double x = sv[f];
-    int less = 0, equal = 0;
-    for (int m = 0; m < F; ++m) {
-      const double y = sv[m];
-      less += (y < x);
-      equal += (y == x);
+  double* out = R + (int64_t)cell * ldr;
+  for (int c0 = 0; c0 < F; c0 += chunk) {
+    const int nc = min(chunk, F - c0);
+    __syncthreads();
+    for (int f = threadIdx.x; f < nc; f += blockDim.x) sv[f] = row[c0 + f];
+    __syncthreads();
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+      const double x = (f >= c0 && f < c0 + nc) ? sv[f - c0] : row[f];
+      int less = 0, equal = 0;
+      for (int m = 0; m < nc; ++m) {
+        const double y = sv[m];
+        less += (y < x);
+        equal += (y == x);
+      }
+      const double part = (double)less + 0.5 * (double)equal;
+      out[f] = (c0 == 0 ? 0.5 : out[f]) + part;
     }
-    R[(int64_t)cell * ldr + f] = (double)less + 0.5 * (double)(equal + 1);
   }
 }
 
@@ -226,15 +234,15 @@ extern "C" int scrna_corr_epilogue_f64(const double* G, int64_t ldg, int N, int 
 extern "C" int scrna_rank_avg_f64(const double* Xt, int64_t ld, int N, int F, double* R, int64_t ldr,
                                   void* stream) {
   if (!Xt || !R || N <= 0 || F <= 0 || ld < F || ldr < F) return SCRNA_ERR_BADARG;
-  const size_t smem = (size_t)F * sizeof(double);
-  if (smem > 220 * 1024) return SCRNA_ERR_UNSUPPORTED;
+  const int chunk = F < 27648 ? F : 27648;
+  const size_t smem = (size_t)chunk * sizeof(double);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(rank_avg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr = true;
   }
   int threads = F >= 1024 ? 1024 : (int)(ceil_div(F, 32) * 32);
-  rank_avg_kernel<<<N, threads, smem, (cudaStream_t)stream>>>(Xt, ld, N, F, R, ldr);
+  rank_avg_kernel<<<N, threads, smem, (cudaStream_t)stream>>>(Xt, ld, N, F, chunk, R, ldr);
   return last_launch_status();
 }
 

@@ -29,18 +29,37 @@ def _svd_flip_u(u, v):
     return u * signs[np.newaxis, :], v * signs[:, np.newaxis]
 
 
+def _chunked(times, width):
+    """`times` handles operands of at most `width` columns (the solver's rank): wider ones go in column chunks."""
+    def f(Q):
+        if Q.shape[1] == width:
+            return times(Q)
+        out = []
+        for c in range(0, Q.shape[1], width):
+            blk = np.zeros((Q.shape[0], width))
+            w = min(width, Q.shape[1] - c)
+            blk[:, :w] = Q[:, c: c + w]
+            out.append(times(blk)[:, :w])
+        return np.concatenate(out, axis=1)
+    return f
+
+
 def randomized_svd_device(prod, k, seed=0, n_oversamples=10):
     """sklearn `_randomized_svd(X, k, random_state=seed)` with `prod.x_times` / `prod.xt_times` as the only
     accesses to X (g x n).  Returns U (g x k), S (k), Vt (k x n)."""
-    g, n = prod.X.g, prod.X.n
+    g = prod.X.g
+    n = prod.cell_range[2] if getattr(prod, "cell_range", None) else prod.X.n
     rng = np.random.RandomState(seed)
     r = k + n_oversamples
     n_iter = 7 if k < 0.1 * min(g, n) else 4
     transpose = g < n                      # sklearn works on M = X^T when X has more columns than rows
+    xt = getattr(prod, "xt_times_full", prod.xt_times)      # global products when the cells are sharded
+    x_times = _chunked(prod.x_times, prod.k)
+    xt_times = _chunked(xt, prod.k)
     if transpose:
-        m_times, mt_times, m_cols = prod.xt_times, prod.x_times, g
+        m_times, mt_times, m_cols = xt_times, x_times, g
     else:
-        m_times, mt_times, m_cols = prod.x_times, prod.xt_times, n
+        m_times, mt_times, m_cols = x_times, xt_times, n
     Q = rng.normal(size=(m_cols, r))
     lu = lambda A: linalg.lu(A, permute_l=True, check_finite=False)[0]
     if n_iter <= 2:
@@ -88,15 +107,22 @@ def nndsvdar_from_svd(U, S, V, xmean, seed=0):
     return W, H
 
 
-def nndsvdar_init_device(dm, k, kernels=None, seed=0, XT=None):
+def nndsvdar_init_device(dm, k, kernels=None, seed=0, XT=None, comm=None, cell_range=None):
     """(W0 g x k, H0 k x n) of NMF(init='nndsvdar', random_state=seed) for the device-resident matrix `dm`.
-    Returns (W0, H0, XT): the transposed copy is handed back so that the NMF solver can reuse it."""
+    Returns (W0, H0, XT): the transposed copy is handed back so that the NMF solver can reuse it.
+
+    With `comm` and `cell_range = (c0, c1, n_total)` the matrix is one cell shard of n_total cells: the products
+    are summed / gathered over the ranks, the tall-skinny host factorizations and the RNG stream are replicated
+    (identical on every rank), and the GLOBAL H0 (k x n_total) is returned -- the caller takes its columns.
+    Ranks above 54 (k + 10 oversamples > 64 components) run the (k + 10)-wide products in chunks of 64 columns."""
     from .nmf_solver import NmfSolver
-    r = k + 10
-    if r > 64:
-        raise ValueError("device NNDSVD init supports k <= 54 (k + 10 oversamples <= 64 components)")
-    prod = NmfSolver(dm, r, kernels=kernels, XT=XT)
+    r = min(k + 10, 64)
+    prod = NmfSolver(dm, r, kernels=kernels, XT=XT, comm=comm)
+    n_total = dm.n
+    if cell_range is not None:
+        prod.set_cell_range(*cell_range)
+        n_total = cell_range[2]
     U, S, Vt = randomized_svd_device(prod, k, seed=seed)
-    xmean = prod.x_sum() / (float(dm.g) * float(dm.n))
+    xmean = prod.x_sum() / (float(dm.g) * float(n_total))
     W0, H0 = nndsvdar_from_svd(U, S, Vt, xmean, seed=seed)
     return W0, H0, prod.XT

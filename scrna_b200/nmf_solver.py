@@ -83,7 +83,9 @@ class DeviceMatrix:
             raise ValueError("expected a genes x cells matrix")
         g, n = arr.shape
         ldx = round_up(max(n, 1), 32)
-        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        dev = device if device is not None else getattr(kernels, "device", None)
+        if dev is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         out = torch.empty((g, ldx), dtype=torch.float32, device=dev)
         if arr.dtype != np.float64:
             arr = np.ascontiguousarray(arr, dtype=np.float64) if arr.dtype != np.float32 else arr
@@ -174,6 +176,15 @@ class TorchDistComm:
 
     def all_reduce(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def gather_cols(self, local, bounds, n_total):
+        """Every rank contributes `local` (r x n_local, the columns bounds[rank]); returns the full r x n_total
+        tensor on every rank (zero-padded sum: payloads here are the small factors, not X)."""
+        t = local.new_zeros((local.shape[0], int(n_total)))
+        c0, c1 = bounds[self.rank]
+        t[:, c0:c1].copy_(local[:, : c1 - c0])
+        self.all_reduce(t)
+        return t
 
     def all_gather_rows(self, full, bounds):
         """`full` (rows x cols) holds this rank's row block bounds[rank]; afterwards every rank holds all blocks."""
@@ -302,6 +313,7 @@ class NmfSolver:
         self.res_out = t.zeros(1, dtype=f64, device=dev)
         self.gpartG = t.zeros(self.nblkG * kp * kp, dtype=f64, device=dev)
         self.gpartC = t.zeros(self.nblkC * kp * kp, dtype=f64, device=dev)
+        self.cell_range = None
         self.fuse_reduce = True   # partial reduction + Gram fused into the update epilogues
         self._g_num_from_R = True
         self.perms = None
@@ -345,9 +357,30 @@ class NmfSolver:
         self.load_C(C0)
 
     # ---- skinny products with the resident X (device NNDSVD init, scrna_b200/nmf_init.py) -------------
+    def set_cell_range(self, c0, c1, n_total):
+        """This shard holds cells [c0, c1) of n_total: `x_times` then takes the GLOBAL (n_total x k) operand and
+        `xt_times_full` returns the global product (device NNDSVD init on cell shards)."""
+        self.cell_range = (int(c0), int(c1), int(n_total))
+
+    def xt_times_full(self, Q):
+        """X^T @ Q over all shards: (n_total x k), identical on every rank."""
+        loc = self.xt_times(Q)
+        if self.comm is None or self.cell_range is None:
+            return loc
+        c0, c1, n_total = self.cell_range
+        t = self.torch
+        full = t.zeros((n_total, loc.shape[1]), dtype=t.float64, device=self.X.data.device)
+        full[c0:c1].copy_(t.from_numpy(loc).to(full.device))
+        self.comm.all_reduce(full)
+        return full.cpu().numpy()
+
     def x_times(self, Q):
-        """X @ Q for a host (n x k) matrix Q of any sign: one sweep of the X^T copy.  Returns g x k fp64."""
-        self.load_C(np.asarray(Q).T)
+        """X @ Q for a host (n x k) matrix Q of any sign: one sweep of the X^T copy.  Returns g x k fp64 (summed
+        over the cell shards).  With a cell range set, Q is the global operand and this shard uses its rows."""
+        Q = np.asarray(Q)
+        if self.cell_range is not None and Q.shape[0] == self.cell_range[2]:
+            Q = Q[self.cell_range[0]: self.cell_range[1]]
+        self.load_C(Q.T)
         keep = self._g_num_from_R
         self._g_num_from_R = True
         self._products_for_G(None)
@@ -538,6 +571,10 @@ class NmfSolver:
             else:
                 if update_C:
                     self._half_C(code, l1_C, l2_C, draws, offC, ctrl)
+                    if not update_G and self.comm is not None and solver == "cd":
+                        # the cell factor alone is updated (fixed dictionary): its violation is the whole stop rule
+                        kn.sum_f64(self.violC, self.nblkC, self.R_scal[0:1])
+                        self.comm.all_reduce(self.R_scal[0:1])
                 if update_G:
                     if update_C:
                         self._products_for_G(ctrl)

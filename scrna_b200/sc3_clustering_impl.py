@@ -85,6 +85,31 @@ def distances(data, gene_ids, metric='euclidean'):
     return _remember(D.cpu().numpy(), D)
 
 
+def da_nmf_distances(data, gene_ids, da_model, reject_ratio=0., metric='euclidean', mixture=0.5, use_H2=True):
+    """Convex combination of the distances of the data and of its dictionary reconstruction W.H2 (or W.H), the
+    latter rescaled to the former's maximum (scRNA/sc3_clustering_impl.py:79-103; unused by the reference's CLI).
+    Both distance matrices come from the device kernels; the returned array is a fresh host array."""
+    if mixture == 0.0:
+        return distances(data, [], metric=metric)
+    W, H, H2 = da_model
+    dist1 = distances(data, [], metric=metric)
+    if use_H2:
+        dist2 = distances(W.dot(H2), [], metric=metric)
+    else:
+        print('Using H instead of H2 for reconstruction.')
+        dist2 = distances(W.dot(H), [], metric=metric)
+    scale = 1.0
+    if np.max(dist2) < 1e-12:
+        if mixture == 1.0:
+            raise Exception('Distances are all close to zero and mixture=1.0. '
+                            'Seems that source and target data do not go well together.')
+        else:
+            print('Warning! Max distance is close to zero.')
+    else:
+        scale = np.max(dist1) / np.max(dist2)
+    return mixture * (dist2 * scale) + (1. - mixture) * dist1
+
+
 def transformations(dm, components=5, method='pca'):
     """(cells x cells matrix rebuilt from the kept components, cells x components right singular vectors)
     of the PCA-scaled or 'spectral' distance matrix (scRNA/sc3_clustering_impl.py:135-203).  The first return

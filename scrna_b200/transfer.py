@@ -105,6 +105,14 @@ class TransferSession:
         self.kn.argmax_cols(self.H64, self.k, X.n, self.ldc, self.labels_dev)
         return self.labels_dev[: X.n].cpu().numpy().astype(np.int64)
 
+    def set_labels(self, labels):
+        """Use the given per-cell labels (a caller-supplied one-hot H2) for `mixed` / `reject_stats`."""
+        t = self.torch
+        lab = np.ascontiguousarray(labels, dtype=np.int32).reshape(-1)
+        if lab.size != self.X.n:
+            raise ValueError("one label per target cell expected")
+        self.labels_dev[: self.X.n].copy_(t.from_numpy(lab).to(self.labels_dev.device))
+
     def H_host(self):
         return self.H64[: self.k, : self.X.n].cpu().numpy().copy()
 

@@ -83,10 +83,11 @@ def unsupervised_acc_kta(X, labels, kernel='linear', param=1.0, center=True, nor
     (scrna_pairwise_f64), centring / normalisation / the three Frobenius products are two O(n^2) device passes
     (csrc/eval_kta.cu) instead of the reference's dense n^3 products.
 
-    `kernel='rbf'` is not on the device.  A labeling with a single cluster makes the centred label kernel vanish
-    and the reference returns rounding noise; 0.0 is returned here."""
-    if kernel != 'linear':
-        raise NotImplementedError("only the linear kernel (the reference CLI's choice) is implemented on the device")
+    `kernel='rbf'` (get_kernel, utils.py:108-124): exp(-|x_i - x_j|^2 / param) is formed in place from the same
+    Gram.  A labeling with a single cluster makes the centred label kernel vanish and the reference returns
+    rounding noise; 0.0 is returned here."""
+    if kernel not in ('linear', 'rbf'):
+        raise ValueError("kernel must be 'linear' or 'rbf'")
     from . import _lib
     from .sc3_device import default_ops
     ops = default_ops()
@@ -101,6 +102,9 @@ def unsupervised_acc_kta(X, labels, kernel='linear', param=1.0, center=True, nor
     ops._call("scrna_pairwise_f64", Xd, n, X.shape[0], n, 1, K, n, ops._s())
     rowsum, diag = ops.empty(n), ops.empty(n)
     ops._call("scrna_kta_rowstats_f64", K, n, n, rowsum, diag, ops._s())
+    if kernel == 'rbf':
+        ops._call("scrna_kta_rbf_f64", K, n, n, diag.clone(), float(param), ops._s())
+        ops._call("scrna_kta_rowstats_f64", K, n, n, rowsum, diag, ops._s())
     rs, dg = rowsum.cpu().numpy(), diag.cpu().numpy()
 
     def params(rowsum_, diag_):
@@ -122,21 +126,74 @@ def unsupervised_acc_kta(X, labels, kernel='linear', param=1.0, center=True, nor
     counts = np.bincount(labels, minlength=int(labels.max()) + 1).astype(np.float64)
     mx, bx, tx, dx = params(rs, dg)
     my, by, ty, dy = params(counts[labels], np.ones(n))
-    if bx is None or by is None:
-        # identity fallback: only the diagonals of the (centred) kernels survive -- O(n) on the host
-        kx = dx if bx is None else np.ones(n)
-        ky = dy if by is None else np.ones(n)
-        den = np.sqrt((kx * kx).sum() * (ky * ky).sum())
-        return float((kx * ky).sum() / den) if den > 0 else 0.0
     dev = lambda a: t.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(ops.dev)
-    part = ops.empty(3 * _lib.call("scrna_kta_blocks"))
-    out = ops.empty(3)
-    lab32 = t.from_numpy(labels.astype(np.int32)).to(ops.dev)
-    ops._call("scrna_kta_align_f64", K, n, n, lab32, dev(mx), dev(bx), float(tx), dev(my), dev(by), float(ty), part,
-              out, ops._s(), launches=2)
-    sxy, sxx, syy = out.cpu().numpy()
+
+    def frobenius(bx_, by_):
+        part = ops.empty(3 * _lib.call("scrna_kta_blocks"))
+        out = ops.empty(3)
+        lab32 = t.from_numpy(labels.astype(np.int32)).to(ops.dev)
+        ops._call("scrna_kta_align_f64", K, n, n, lab32, dev(mx), dev(bx_), float(tx), dev(my), dev(by_), float(ty),
+                  part, out, ops._s(), launches=2)
+        return out.cpu().numpy()          # <Kx, Ky>, <Kx, Kx>, <Ky, Ky>
+
+    if bx is None and by is None:
+        # normalize_kernel's identity fallback on both sides (utils.py:71-73): only the diagonals survive
+        den = np.sqrt((dx * dx).sum() * (dy * dy).sum())
+        return float((dx * dy).sum() / den) if den > 0 else 0.0
+    if bx is None or by is None:
+        # one side fell back to diag(d): <diag(d), Kn> = sum d_i (the normalised side has a unit diagonal), but
+        # <Kn, Kn> is the FULL Frobenius norm of the normalised side -- from the device pass
+        ones = np.ones(n)
+        _, sxx, syy = frobenius(ones if bx is None else bx, ones if by is None else by)
+        d_fb, s_ok = (dx, syy) if bx is None else (dy, sxx)
+        den = np.sqrt((d_fb * d_fb).sum() * s_ok)
+        return float(d_fb.sum() / den) if den > 0 else 0.0
+    sxy, sxx, syy = frobenius(bx, by)
     den = np.sqrt(sxx * syy)
     return float(sxy / den) if den > 0 else 0.0
+
+
+# ---- small host helpers of the reference's evaluation code (scRNA/utils.py:66-124), kept for API completeness:
+# O(n^2) element-wise / closed forms instead of the reference's dense n^3 products; unused by the hot path ----------
+def normalize_kernel(K):
+    N = K.shape[0]
+    a = np.sqrt(np.diag(K)).reshape((N, 1))
+    if np.any(np.isnan(a)) or np.any(np.isinf(a)) or np.any(np.abs(a) <= 1e-16):
+        print('Numerical instabilities.')
+        C = np.eye(N)
+    else:
+        b = 1. / a
+        C = b.dot(b.T)
+    return K * C
+
+
+def center_kernel(K):
+    """K - 1K/N - K1/N + 1K1/N^2 via row / column means (the reference forms three N^3 products, utils.py:79-83)."""
+    K = np.asarray(K, dtype=np.float64)
+    return K - K.mean(axis=0, keepdims=True) - K.mean(axis=1, keepdims=True) + K.mean()
+
+
+def kta_align_general(K1, K2):
+    """<K1, K2>_F / sqrt(<K1, K1>_F <K2, K2>_F)  (utils.py:86-95, traces of products there)."""
+    return float(np.sum(K1 * K2) / np.sqrt(np.sum(K1 * K1) * np.sum(K2 * K2)))
+
+
+def kta_align_binary(K, y):
+    """Alignment of K with the label kernel y y^T, y in {+1, -1}^m (utils.py:98-103)."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    m = y.size
+    return float(y.dot(K).dot(y) / (m * np.sqrt(np.sum(K * K))))
+
+
+def get_kernel(X, Y, type='linear', param=1.0):
+    """Kernel between the columns of X and Y (dims x examples), utils.py:106-124."""
+    if type == 'linear':
+        return X.T.dot(Y)
+    if type == 'rbf':
+        dx = np.sum(X * X, axis=0).reshape(-1, 1)
+        dy = np.sum(Y * Y, axis=0).reshape(1, -1)
+        return np.exp(-(dx - 2. * X.T.dot(Y) + dy) / param)
+    return 1.0
 
 
 def get_transferability_score(W, H, trg_data, reps=100, alpha=0.0, l1=0.75, max_iter=100, rel_err=1e-3):

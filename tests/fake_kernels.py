@@ -20,6 +20,7 @@ class FakeKernels:
 
     def __init__(self):
         self.torch = torch
+        self.device = torch.device("cpu")
         self.launches = 0
         self.sweep_events = None
 

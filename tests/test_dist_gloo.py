@@ -184,3 +184,71 @@ def test_sc3_kmeans_ensemble_sharded_world2():
     ret = mgr.dict()
     mp.spawn(_sc3_worker, args=(world, port, ret), nprocs=world, join=True)
     assert [ret[r] for r in range(world)] == [True, True]
+
+
+def _class_worker(rank, world, port, case, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_kernels import FakeKernels
+        from oracle import nmf_oracle as no
+        import scrna_b200.nmf_clustering as nc
+        from scrna_b200.nmf_solver import DeviceMatrix, NmfSolver, TorchDistComm, shard_bounds
+        kn = FakeKernels()
+        nc._kernels = lambda: kn                       # the classes' compute provider (test stand-in)
+        comm = TorchDistComm()
+        rng = np.random.RandomState(5)
+        g, n, k = 50, 91, 4
+        lab = rng.randint(0, k, size=n)
+        lab[:k] = np.arange(k)
+        mu = rng.gamma(2.0, 1.0, size=(g, k))[:, lab] * (0.5 + rng.rand(1, n))
+        X = rng.poisson(mu).astype(np.float64) + 1.0 * (rng.rand(g, n) < 0.05)
+        ids = np.arange(g)
+        rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+        if case == "nmf":
+            Wr, Hr, lr, nr = no.nmf_clustering_apply(X, k, alpha=2.0, l1=0.5, max_iter=60, rel_err=1e-3)
+            obj = nc.NmfClustering(X, ids, k)
+            obj.apply(k=k, alpha=2.0, l1=0.5, max_iter=60, rel_err=1e-3, comm=comm)
+            ok = (obj.n_iter == nr and rel(obj.dictionary, Wr) < 1e-4 and rel(obj.data_matrix, Hr) < 1e-4
+                  and np.array_equal(obj.cluster_labels, lr) and obj.data_matrix.shape == (k, n))
+        elif case == "nmf_sharded_device_init":
+            Wr, Hr, lr, nr = no.nmf_clustering_apply(X, k, alpha=2.0, l1=0.5, max_iter=60, rel_err=1e-3)
+            c0, c1 = shard_bounds(n, world, rank)
+            obj = nc.NmfClustering(X[:, c0:c1], ids, k)          # this rank only ever sees its cells
+            obj.apply(k=k, alpha=2.0, l1=0.5, max_iter=60, rel_err=1e-3, comm=comm, cells="sharded", init="device")
+            ok = (abs(obj.n_iter - nr) <= 1 and rel(obj.dictionary, Wr) < 1e-3
+                  and rel(obj.data_matrix, Hr[:, c0:c1]) < 1e-3 and np.array_equal(obj.cluster_labels, lr[c0:c1]))
+        elif case == "initw":
+            Dr, Mr, lr, nr = no.nmf_clustering_initw_apply(X, lab, k, alpha=2.0, l1=0.5, max_iter=60, rel_err=1e-3)
+            obj = nc.NmfClustering_initW(X, ids, k, lab)
+            obj.apply(k=k, alpha=2.0, l1=0.5, max_iter=60, rel_err=1e-3, comm=comm)
+            ok = (tuple(obj.n_iter) == tuple(nr) and rel(obj.dictionary, Dr) < 1e-4 and rel(obj.data_matrix, Mr) < 1e-4
+                  and np.array_equal(obj.cluster_labels, lr))
+        else:   # fixed dictionary, cell factor alone updated, cells sharded (the violation was never
+            #     all-reduced on this path and the fit stopped after one iteration)
+            W = np.abs(rng.randn(g, k)) + 0.1
+            Ht, _, nr, _ = no.nmf_cd(X.T, np.zeros((n, k)), W.T.copy(), 0, 0, 0, 0, tol=1e-4, max_iter=80, update_H=False)
+            c0, c1 = shard_bounds(n, world, rank)
+            slv = NmfSolver(DeviceMatrix.from_host(X[:, c0:c1], kn), k, kernels=kn, comm=comm)
+            res = slv.fit(W, np.zeros((k, c1 - c0)), solver="cd", tol=1e-4, max_iter=80, update_G=False, update_C=True,
+                          first="C", seed=0, shuffle=True)
+            ok = res.n_iter == nr and nr > 2 and rel(res.C, Ht.T[:, c0:c1]) < 1e-6
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["nmf", "nmf_sharded_device_init", "initw", "fixed_dictionary_cd"])
+def test_class_api_cells_sharded_world2(case):
+    """NmfClustering / NmfClustering_initW .apply(comm=) with the cells sharded over two ranks (replicated and
+    pre-sharded input, host and device NNDSVDar init) against the single-process oracle, and the fixed-dictionary
+    sharded CD solve."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_class_worker, args=(world, port, case, ret), nprocs=world, join=True)
+    assert [ret.get(r) for r in range(world)] == [True, True]

@@ -75,3 +75,54 @@ def test_kta_score_vs_reference_golden(kernels, golden, name):
             ref = float(g["%s_kta_c%d_n%d" % (name, c, nrm)])
             got = unsupervised_acc_kta(X, lab, center=c, normalize=nrm)
             assert abs(got - ref) < 1e-10, (name, c, nrm, got, ref)
+
+
+def test_kta_rbf_kernel_and_one_sided_fallback(kernels):
+    """unsupervised_acc_kta(kernel='rbf') (scRNA/utils.py:108-124, 137-139) against the closed-form restatement, and
+    the mixed case of normalize_kernel's identity fallback (one all-zero cell: its centred diagonal is fine but a
+    constant-zero label kernel row is not) where the reference takes the FULL Frobenius norm of the normalised side."""
+    from oracle import eval_oracle as eo
+    from scrna_b200.utils import unsupervised_acc_kta
+    rng = np.random.RandomState(9)
+    X = rng.poisson(2.0, size=(40, 30)).astype(np.float64)
+    lab = rng.randint(0, 3, size=30)
+    Y = np.zeros((30, 3)); Y[np.arange(30), lab] = 1
+    sq = (X * X).sum(0)
+    for param in (50.0, 400.0):
+        Kx = np.exp(-(sq[:, None] - 2 * X.T @ X + sq[None, :]) / param)
+        Ky = Y @ Y.T
+        for c in (True, False):
+            for nrm in (True, False):
+                a, b = (eo.center_kernel(Kx), eo.center_kernel(Ky)) if c else (Kx, Ky)
+                if nrm:
+                    a, b = eo.normalize_kernel(a), eo.normalize_kernel(b)
+                ref = float((a * b).sum() / np.sqrt((a * a).sum() * (b * b).sum()))
+                got = unsupervised_acc_kta(X, lab, kernel='rbf', param=param, center=c, normalize=nrm)
+                assert abs(got - ref) < 1e-10, (param, c, nrm, got, ref)
+    # linear kernel without centring and an all-zero cell: Kx has a zero diagonal entry -> identity fallback for Kx only
+    X0 = X.copy(); X0[:, 4] = 0.0
+    ref = eo.unsupervised_acc_kta(X0, lab, center=False, normalize=True)
+    got = unsupervised_acc_kta(X0, lab, center=False, normalize=True)
+    assert abs(got - ref) < 1e-10, (got, ref)
+
+
+def test_reject_classifier_matches_reference_formula(kernels):
+    """DaNmfClustering.reject_classifier (scRNA/nmf_clustering.py:274-295) against the formulas it is built from."""
+    from oracle import eval_oracle as eo
+    from scrna_b200 import DaNmfClustering, NmfClustering
+    rng = np.random.RandomState(3)
+    X = rng.poisson(2.0, size=(30, 25)).astype(np.float64)
+    K = X.T @ X
+    kurts = rng.rand(25)
+    da = DaNmfClustering(NmfClustering(X, np.arange(30), 2), X, np.arange(30), 2)
+    got = da.reject_classifier(K, kurts)
+    Kn = eo.normalize_kernel(eo.center_kernel(K))
+    sinds = np.argsort(kurts)
+    best, best_i = -1.0, -1
+    for i in range(K.shape[1] - 2):
+        y = np.ones(25); y[sinds[:i + 1]] = -1
+        kta = (Kn * np.outer(y, y)).sum() / (25 * np.sqrt((Kn * Kn).sum()))
+        if kta > best:
+            best, best_i = kta, i + 1
+    ref = np.ones(25, dtype=int); ref[sinds[:best_i]] = -1
+    np.testing.assert_array_equal(got, ref)

@@ -53,6 +53,41 @@ def test_rank_average_with_ties(ops):
     np.testing.assert_allclose(S, so.distances(X, "spearman"), rtol=0, atol=1e-12)
 
 
+def test_rank_average_more_genes_than_one_shared_memory_chunk(ops):
+    """Round 1 returned UNSUPPORTED above 28 160 genes: the ranks are now counted against the gene vector in chunks."""
+    rng = np.random.RandomState(2)
+    X = rng.poisson(1.5, size=(30011, 7)).astype(np.float64)          # heavy ties, genes > one 27 648-gene chunk
+    S = ops.distances(X, "spearman").cpu().numpy()
+    np.testing.assert_allclose(S, so.distances(X, "spearman"), rtol=0, atol=1e-12)
+
+
+def test_da_nmf_distances_vs_reference_formula(ops):
+    """scRNA/sc3_clustering_impl.py:79-103: convex combination of the data's distances and the rescaled distances of
+    its dictionary reconstruction; and in-place edits of a stage result raise instead of desynchronising the device
+    twin."""
+    from scrna_b200 import sc3_clustering_impl as sc
+    rng = np.random.RandomState(4)
+    g, n, k = 60, 45, 3
+    W, H = np.abs(rng.randn(g, k)), np.abs(rng.randn(k, n))
+    H2 = np.zeros((k, n)); H2[np.argmax(H, 0), np.arange(n)] = 1
+    X = rng.poisson(W @ H * 3).astype(np.float64)
+    for use_H2 in (True, False):
+        got = sc.da_nmf_distances(X, None, (W, H, H2), metric="euclidean", mixture=0.3, use_H2=use_H2)
+        d1 = so.distances(X, "euclidean")
+        d2 = so.distances(W @ (H2 if use_H2 else H), "euclidean")
+        ref = 0.3 * d2 * (d1.max() / d2.max()) + 0.7 * d1
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13)
+        got[0, 0] = 1.0                                    # a fresh, writable host array
+    np.testing.assert_array_equal(sc.da_nmf_distances(X, None, (W, H, H2), mixture=0.0), so.distances(X, "euclidean"))
+    D = sc.distances(X, None)
+    with pytest.raises(ValueError):
+        D /= D.max()                                       # would leave the resident device copy stale
+    Dc = D / D.max()                                       # a copy has no device twin: uploaded as it is
+    _, V1 = sc.transformations(Dc, components=5)
+    _, V2 = sc.transformations(Dc.copy(), components=5)
+    np.testing.assert_array_equal(V1, V2)
+
+
 @pytest.mark.parametrize("metric", ["euclidean", "pearson", "spearman"])
 @pytest.mark.parametrize("method", ["pca", "spectral"])
 def test_transformations_vs_reference(ops, sc3g, metric, method):
