@@ -216,6 +216,12 @@ int scrna_cast_f64_f32(const double* src, float* dst, int64_t count, void* strea
 int scrna_convert_pad_f64_f32(const double* src, int64_t ld_src, float* dst, int64_t ld_dst,
                               int64_t rows, int64_t cols, void* stream);
 
+/* ---- pre-processing filters (cell_filter / gene_filter, sc3_clustering_impl.py:32-58) over a band of the fp64
+ * host-layout matrix: col_ge[c] += #{r: X[r][c] >= thr} (accumulated over bands: zero it first), row_ge[r] =
+ * #{c: X[r][c] >= thr}, row_gt0[r] = #{c: X[r][c] > 0}; NaN counts as 0 and raises nan_flag[0]. */
+int scrna_filter_counts_f64(const double* X, int64_t ld, int64_t rows, int64_t cols, double thr, int32_t* col_ge,
+                            int32_t* row_ge, int32_t* row_gt0, int32_t* nan_flag, void* stream);
+
 /* ---- residuals (K7): sum_{i,j} |X - G.C|^p over the whole shard, p = 1 (utils.py:202, target
  * transfer error) or p = 2 (squared Frobenius, _nmf.py:866-879 convergence test of solver='mu').
  * partials: scrna_residual_blocks(ncols, kp) doubles; out: 1 double (fixed-order sum). */

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "scrna_convert_pad_f64_f32": [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr],
     "scrna_residual_blocks": [c_i64, c_int],
     "scrna_residual": [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr],
+    "scrna_filter_counts_f64": [c_ptr, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_sum_f64": [c_ptr, c_int, c_ptr, c_dbl, c_ptr],
     "scrna_transfer_mu_step": [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_i64, c_i64, c_ptr, c_ptr],
     "scrna_argmax_cols": [c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr],

@@ -378,3 +378,54 @@ extern "C" int scrna_reject_stats(const float* X, int64_t ldx, int g, int64_t nc
       X, ldx, g, ncols, G64, k, kp, H64, ldc, labels, out, ldo);
   return last_launch_status();
 }
+
+// ---- pre-processing filters on the device ------------------------------------------
+// One pass over a band of the fp64 host-layout matrix (rows x cols): per-column counts of entries >= thr
+// (cell_filter, sc3_clustering_impl.py:32-42), per-row counts of entries >= thr and of entries > 0 (gene_filter,
+// :45-58).  NaN counts as 0, as after the reference's in-place `data[np.isnan(data)] = 0`; nan_flag is raised so
+// that the caller can apply that in-place zeroing to the host matrix only when there is something to zero.
+// One CTA per row: row counts by block reduction, column counts by integer atomics (order-free, exact).
+namespace scrna {
+__global__ void __launch_bounds__(256)
+filter_counts_kernel(const double* __restrict__ X, int64_t ld, int64_t rows, int64_t cols, double thr,
+                     int32_t* __restrict__ col_ge, int32_t* __restrict__ row_ge, int32_t* __restrict__ row_gt0,
+                     int32_t* __restrict__ nan_flag) {
+  __shared__ int sge[8], sgt[8];
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const double* x = X + r * ld;
+    int ge = 0, gt = 0;
+    bool nan_seen = false;
+    for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
+      double v = x[c];
+      if (v != v) { nan_seen = true; v = 0.0; }
+      if (v >= thr) { ++ge; atomicAdd(col_ge + c, 1); }
+      gt += (v > 0.0);
+    }
+    if (nan_seen) atomicOr(nan_flag, 1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ge += __shfl_xor_sync(0xffffffffu, ge, o);
+      gt += __shfl_xor_sync(0xffffffffu, gt, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { sge[threadIdx.x >> 5] = ge; sgt[threadIdx.x >> 5] = gt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int a = 0, b = 0;
+      for (int w = 0; w < 8; ++w) { a += sge[w]; b += sgt[w]; }
+      row_ge[r] = a;
+      row_gt0[r] = b;
+    }
+  }
+}
+}  // namespace scrna
+
+extern "C" int scrna_filter_counts_f64(const double* X, int64_t ld, int64_t rows, int64_t cols, double thr,
+                                       int32_t* col_ge, int32_t* row_ge, int32_t* row_gt0, int32_t* nan_flag,
+                                       void* stream) {
+  if (!X || !col_ge || !row_ge || !row_gt0 || !nan_flag || rows <= 0 || cols <= 0 || ld < cols) return SCRNA_ERR_BADARG;
+  int64_t grid = rows < (int64_t)num_sms() * 8 ? rows : (int64_t)num_sms() * 8;
+  filter_counts_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(X, ld, rows, cols, thr, col_ge, row_ge, row_gt0,
+                                                                       nan_flag);
+  return last_launch_status();
+}

@@ -285,7 +285,10 @@ class DaNmfClustering(NmfClustering):
         self.comm = comm if (comm is not None and comm.world > 1) else None
 
     def get_mixed_data(self, mix=0.0, reject_ratio=0., use_H2=True, calc_transferability=False, max_iter=100,
-                       rel_err=1e-3, H_init=None):
+                       rel_err=1e-3, H_init=None, _target_cache=None):
+        """Reference signature (nmf_clustering.py:147) plus opt-in `H_init` (inject the start instead of drawing
+        it) and `_target_cache` (a dict shared by the caller between calls on the SAME target data: the uploaded
+        target matrix is kept in it, so a (k, mixture) grid uploads it once -- scrna_b200/workflows.py)."""
         trg_data = self.pre_processing()
         trg_gene_ids = self.gene_ids[self.remain_gene_inds]
         src_gene_ids = self.src.gene_ids[self.src.remain_gene_inds].copy()
@@ -300,7 +303,13 @@ class DaNmfClustering(NmfClustering):
         n_t = trg_data.shape[1]
         kn = _kernels()
         part = _Cells(n_t, self.comm, 'replicated')
-        sess = TransferSession(W, part.local(trg_data), kernels=kn, comm=part.comm)
+        trg_dev = part.local(trg_data)
+        if _target_cache is not None:
+            key = (trg_data.shape, tuple(np.asarray(inds1[:8]).tolist()), int(np.asarray(inds1).sum()), part.c0, part.c1)
+            if key not in _target_cache:
+                _target_cache[key] = DeviceMatrix.from_host(trg_dev, kn)
+            trg_dev = _target_cache[key]
+        sess = TransferSession(W, trg_dev, kernels=kn, comm=part.comm)
         H0 = transfer_h_init(k, n_t) if H_init is None else np.asarray(H_init, dtype=np.float64)   # global RNG draw
         sess.solve(part.local(H0), max_iter=max_iter, rel_err=rel_err)
         H = part.gather(sess.H_host(), kn)

@@ -8,21 +8,58 @@ consensus matrix, consensus clustering).
 import numpy as np
 
 
+DEVICE_FILTER_MIN_ELEMENTS = 1 << 24   # below this the NumPy passes cost milliseconds
+
+
+def _filter_counts(data, non_zero_threshold):
+    """(col_ge, row_ge, row_gt0) of the genes x cells matrix: counts of entries >= threshold per cell and per gene,
+    and of entries > 0 per gene, NaNs zeroed IN PLACE in the caller's matrix as the reference does (:38-39, :51-52).
+    Large matrices on a GPU box stream through the device in row bands (scrna_filter_counts_f64: one pass, integer
+    counts -- identical to NumPy's); the host matrix is only touched when a NaN was actually seen."""
+    big = data.size >= DEVICE_FILTER_MIN_ELEMENTS and data.dtype == np.float64 and data.ndim == 2
+    if big:
+        try:
+            import torch
+            big = torch.cuda.is_available()
+        except Exception:
+            big = False
+    if not big:
+        data[np.isnan(data)] = 0
+        return (np.sum(data >= non_zero_threshold, axis=0), np.sum(data >= non_zero_threshold, axis=1),
+                np.sum(data > 0, axis=1))
+    from . import _lib
+    ops = _ops()
+    t = ops.torch
+    g, n = data.shape
+    i32 = t.int32
+    col_ge = ops.zeros(n, dtype=i32)
+    row_ge = ops.zeros(g, dtype=i32)
+    row_gt0 = ops.zeros(g, dtype=i32)
+    flag = ops.zeros(1, dtype=i32)
+    rows_per_band = max(1, int((256 << 20) // max(1, n * 8)))
+    for r0 in range(0, g, rows_per_band):
+        r1 = min(g, r0 + rows_per_band)
+        band = t.from_numpy(np.ascontiguousarray(data[r0:r1])).to(ops.dev)
+        ops._call("scrna_filter_counts_f64", band, n, r1 - r0, n, float(non_zero_threshold), col_ge, row_ge[r0:r1],
+                  row_gt0[r0:r1], flag, ops._s())
+    if int(flag.cpu()[0]):
+        data[np.isnan(data)] = 0
+    return (col_ge.cpu().numpy().astype(np.int64), row_ge.cpu().numpy().astype(np.int64),
+            row_gt0.cpu().numpy().astype(np.int64))
+
+
 def cell_filter(data, num_expr_genes=2000, non_zero_threshold=2):
     """Indices of cells expressing at least `num_expr_genes` genes at >= non_zero_threshold.
     NaNs are zeroed IN PLACE in the caller's matrix, as the reference does (:38-39)."""
-    data[np.isnan(data)] = 0
-    res = np.sum(data >= non_zero_threshold, axis=0)
+    res, _, _ = _filter_counts(data, non_zero_threshold)
     return np.where(np.isfinite(res) & (res >= num_expr_genes))[0]
 
 
 def gene_filter(data, perc_consensus_genes=0.94, non_zero_threshold=2):
     """Indices of genes that are neither rare nor ubiquitous (:45-58): at least n*(1-p) cells at
     >= threshold and at most n*p cells above zero.  NaNs zeroed in place."""
-    data[np.isnan(data)] = 0
+    _, res_l, res_h = _filter_counts(data, non_zero_threshold)
     num_cells = data.shape[1]
-    res_l = np.sum(data >= non_zero_threshold, axis=1)
-    res_h = np.sum(data > 0, axis=1)
     lower_bound = float(num_cells) * (1. - perc_consensus_genes)
     upper_bound = float(num_cells) * perc_consensus_genes
     return np.where((res_l >= lower_bound) & (res_h <= upper_bound))[0]

@@ -126,3 +126,57 @@ def test_reject_classifier_matches_reference_formula(kernels):
             best, best_i = kta, i + 1
     ref = np.ones(25, dtype=int); ref[sinds[:best_i]] = -1
     np.testing.assert_array_equal(got, ref)
+
+
+def test_target_workflow_matches_the_reference_cli_loop(kernels, default_sim, golden, tmp_path):
+    """Row f2: scrna_b200.workflows.target_workflow (cmd_target.py:179-260 as a library call; target uploaded once
+    for the whole mixture grid) against tests/golden/workflow.npz, produced by the same loop over the UNMODIFIED
+    reference classes: identical labels for every mixture, KTA to 1e-5, identical ARI, identical KTA-optimal mixture;
+    the source model travels through the reference-compatible `.npz`."""
+    from scrna_b200.workflows import source_workflow, target_workflow
+    g = golden("workflow")
+    gene_ids = default_sim["gene_ids"]
+    src = source_workflow(default_sim["src"], gene_ids, default_sim["src_labels"], gene_ids, cluster_range=(7,),
+                          fout=str(tmp_path / "src"))
+    model, kta, _ = src[7]
+    np.testing.assert_array_equal(model.cluster_labels, g["src_labels_out"])
+    assert abs(kta - float(g["src_kta"])) < 1e-9
+    assert (tmp_path / "src_c7.npz").exists() and (tmp_path / "src_c7.labels.tsv").exists()
+    mixtures = [float(m) for m in g["mixtures"]]
+    launches0 = kernels.launches
+    np.random.seed(int(g["seed"]))
+    out = target_workflow(str(tmp_path / "src_c7.npz"), default_sim["trg"], gene_ids, gene_ids, cluster_range=(7,),
+                          mixtures=mixtures, labels=default_sim["trg_labels"], fout=str(tmp_path / "trg"))
+    np.testing.assert_array_equal(out["trg_labels"].astype(np.int32), g["trg_labels"])
+    # the mixed data carries our dictionary (within the 1e-3 per-factor budget of the reference's): KTA to 1e-5;
+    # mixture 0 is the untouched target: exact
+    np.testing.assert_allclose(out["accs"][0], g["accs"][0], rtol=0, atol=1e-5)
+    assert abs(out["accs"][0, 0, 0] - g["accs"][0, 0, 0]) < 1e-10
+    np.testing.assert_allclose(out["accs"][1], g["accs"][1], rtol=0, atol=1e-12)
+    assert int(out["opt_mix_ind"][0]) == int(np.argmax(g["accs"][0, 0]))
+    assert kernels.launches > launches0
+    lab_file = np.loadtxt(str(tmp_path / "trg_c7.labels.transfercluster.tsv"), delimiter="\t")
+    np.testing.assert_array_equal(lab_file[0].astype(np.int64), out["pred_labels"][7])
+
+
+def test_device_filters_match_numpy_and_keep_the_nan_quirk(kernels, monkeypatch):
+    """Row f4: cell_filter / gene_filter over row bands on the device (one pass, integer counts) return exactly the
+    NumPy indices, and NaNs are still zeroed in place in the caller's matrix (sc3_clustering_impl.py:38-39, 51-52)."""
+    from scrna_b200 import sc3_clustering_impl as sc
+    rng = np.random.RandomState(8)
+    X = rng.poisson(rng.uniform(0.05, 3.0, size=(700, 1)) * rng.uniform(0.5, 1.5, size=(1, 900))).astype(np.float64)
+    X[rng.rand(700, 900) < 0.001] = np.nan
+    host, dev = X.copy(), X.copy()
+    n_expr = int(np.median(np.nansum(X >= 2, axis=0)))
+    monkeypatch.setattr(sc, "DEVICE_FILTER_MIN_ELEMENTS", 1 << 62)
+    ref_cells = sc.cell_filter(host, num_expr_genes=n_expr, non_zero_threshold=2)
+    ref_genes = sc.gene_filter(host, perc_consensus_genes=0.8, non_zero_threshold=2)
+    monkeypatch.setattr(sc, "DEVICE_FILTER_MIN_ELEMENTS", 1)
+    l0 = kernels.launches
+    got_cells = sc.cell_filter(dev, num_expr_genes=n_expr, non_zero_threshold=2)
+    assert kernels.launches > l0 and not np.isnan(dev).any()
+    got_genes = sc.gene_filter(dev, perc_consensus_genes=0.8, non_zero_threshold=2)
+    np.testing.assert_array_equal(got_cells, ref_cells)
+    np.testing.assert_array_equal(got_genes, ref_genes)
+    np.testing.assert_array_equal(dev, host)
+    assert 0 < ref_cells.size < 900 and 0 < ref_genes.size < 700
