@@ -580,6 +580,14 @@ def run_gpu(args):
         shutdown_distributed(world)
         return
     slv_tc, slv_half, slv_kp, payload = bool(slv.tc), bool(slv.half), slv.kp, int(slv.R.numel())
+    if getattr(slv, "fused", False):
+        nb = kn.h_nb(slv.kp, slv.h_parts)
+        exchange = ("fused gene step (nmf_step.cu): %d B of NVLink peer loads + %d B of peer stores per rank per iteration "
+                    "inside one kernel, %s" % (slv.kp * genes * 8 + world * slv.kp * slv.kp * 8,
+                                               genes * (slv.kp * 12 + nb * 2) * (world - 1) // max(world, 1),
+                                               "torch symmetric memory, no NCCL in the loop" if slv.p2p else "single rank"))
+    else:
+        exchange = "one NCCL all-reduce of %d fp64 per iteration" % payload
     slv.release()
     Xh = torch.empty((genes, n_loc), dtype=torch.float32).pin_memory()
     Xh.copy_(Xd[:, :n_loc])
@@ -650,8 +658,7 @@ def run_gpu(args):
                                  "tcgen05 3xTF32 (kp=%d)" % slv_kp if slv_tc else "fp32 FMA (kp=%d)" % slv_kp),
                        "l2_flush": "none needed: each sweep streams %.1f GB per GPU, far larger than the 126 MB L2"
                                    % (genes * n_loc * xbytes / 1e9),
-                       "parallelism": "cells sharded x%d, one all-reduce of %d fp64 per iteration"
-                                      % (world, payload) if world > 1 else "single GPU"},
+                       "parallelism": "cells sharded x%d, %s" % (world, exchange) if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "frobenius_error_after_timed_steps": fro_after,
             "launch": {"mode": "cuda graph replay (one graph per iteration)" if (ms_graph is not None and ms == ms_graph)

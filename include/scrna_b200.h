@@ -124,23 +124,23 @@ int scrna_nmf_tc_shadow(const double* F64, int64_t ld, int64_t rows, int k, int 
  * Same contract and partial layout as scrna_nmf_wtx_partial with kp = kq = k rounded up to 8.  The factor is
  * passed as its `parts`-part (2 or 3) fp16 operand shadow Fh (scrna_nmf_h_shadow_elems(g, kq, parts) halves,
  * K-major MMA operand layout [(r/8)][n < NB][r%8], n = part*kq + t, NB = scrna_nmf_h_nb) of the factor scaled per
- * component by a power of two; inv_scale[t] (kq floats) undoes the scale when the partial is stored.  Both are
- * written by scrna_nmf_h_shadow / scrna_nmf_update.  x * part is exact in the fp32 accumulator; tensor memory
- * is drained every 256 rows into register totals.  nsplit from scrna_nmf_wtx_h_splits.
- * flags bits 8-23: drain period override in stages of 64 rows. */
+ * component and per group of 128 rows by a power of two; inv_scale[(r/128)*kq + t] (scrna_nmf_h_groups(g) x kq
+ * floats) undoes the scale when tensor memory is drained (every 128 rows, into register totals).  Both are
+ * written by scrna_nmf_h_shadow / scrna_nmf_update / the fused step kernels.  x * part is exact in the fp32
+ * accumulator.  nsplit from scrna_nmf_wtx_h_splits (row spans are multiples of 128). */
 int scrna_nmf_h_supported(int kq);
 int scrna_nmf_h_nb(int kq, int parts);
 int64_t scrna_nmf_h_shadow_elems(int64_t rows, int kq, int parts);
+int64_t scrna_nmf_h_groups(int64_t rows);
 int64_t scrna_f16_panel_rows(int64_t rows);
 int64_t scrna_f16_panel_elems(int64_t rows, int64_t cols);
 int scrna_nmf_wtx_h_splits(int g, int64_t ncols, int kq, int parts);
 int scrna_nmf_wtx_partial_h(const void* X16, int64_t rows_pad, int g, int64_t ncols, const void* Fh,
                             const float* inv_scale, int kq, int parts, float* part, int64_t ldc, int nsplit,
                             int flags, const scrna_nmf_ctrl_t* ctrl, void* stream);
-/* fp16 operand shadow of a component-major fp64 master (kp-stride Gram partials give the scale):
- * scale_t = 2^e with ||F[:, t]|| * scale_t in [2^12, 2^13), ||.||^2 = sum over the `nblk` partial Grams
- * gram_parts[p*kp*kp + t*kp + t] (nblk = 1: a finished kp x kp Gram).  gram_out != NULL additionally finishes
- * the kp x kp Gram itself (fixed-order sum of the partials) in the same launch. */
+/* fp16 operand shadow of a component-major fp64 master: per component and 128-row group, scale = 2^e with
+ * max|F| * scale in [2^13, 2^14).  gram_out != NULL additionally finishes a kp x kp Gram (fixed-order sum of the
+ * `nblk` partials gram_parts[p*kp*kp + ...]) in the same launch. */
 int scrna_nmf_h_shadow(const double* F64, int64_t ld, int64_t rows, int k, int kq, int parts,
                        const double* gram_parts, int nblk, int kp, double* gram_out, void* Fh, float* inv_scale,
                        const scrna_nmf_ctrl_t* ctrl, void* stream);
@@ -150,6 +150,27 @@ int scrna_f16_inexact(const float* X, int64_t count, int32_t* inexact, void* str
  * (cols x rows); dst holds scrna_f16_panel_elems(rows, cols) resp. (cols, rows) halves, padding zeroed here. */
 int scrna_narrow_f32_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst, void* stream);
 int scrna_transpose_f32_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst, void* stream);
+
+/* Fused half steps of the MU iteration on the 16-bit path: iteration = sweep(X^T) -> gstep -> sweep(X) -> cstep.
+ * gstep (gene factor, one launch per iteration on every rank, the cross-GPU exchange INSIDE the kernel): reduces
+ * this rank's sweep partials PA (SA x kq x ldg) and its cell-side Gram partials gpartC (groupsC x kq*kq) into the
+ * rank's exchange buffer, synchronises with the peers through arrival flags stored into their memory, sums all
+ * ranks' contributions for ITS gene groups (128 rows each, dealt contiguously over the ranks) with peer loads,
+ * applies W *= XHt / (W.HHt + l1 + l2 W) (sklearn _nmf.py:521-626) and stores the new rows -- fp64 master, fp32
+ * shadow, fp16 operand shadow + 2^-e, per-group Gram partial -- into EVERY rank's arena with peer stores, then
+ * finishes G^T.G locally.  `peers`: device array of nranks 64-bit base addresses of the ranks' arenas (identical
+ * layout; torch symmetric memory; one rank: its own arena); off_*: byte offsets inside an arena: xch fp64
+ * [kq*ldg + kq*kq], sync u32[64] (zeroed once), G64 fp64 [kq*ldg], Gs32 fp32 [g*kq], Gh (scrna_nmf_h_shadow_elems
+ * halves), Ginv fp32 [groups*kq], gpart fp64 [groups*kq*kq], gtg fp64 [kq*kq]; groups = scrna_nmf_step_groups(g).
+ * cstep (cell factor, local): split-partial reduction, MU ratio, all shadows and per-group Gram partials. */
+int scrna_nmf_step_groups(int64_t rows);
+int scrna_nmf_gstep_mu(const void* peers, int nranks, int rank, int64_t off_xch, int64_t off_sync, int64_t off_G64,
+                       int64_t off_Gs32, int64_t off_Gh, int64_t off_Ginv, int64_t off_gpart, int64_t off_gtg, int g,
+                       int64_t ldg, int k, int kq, int nb, int parts, double l1, double l2, const float* PA, int SA,
+                       const double* gpartC, int groupsC, int32_t* nan_flag, void* stream);
+int scrna_nmf_cstep_mu(double* C64, int64_t ldn, int64_t n, int k, int kq, int nb, int parts, const float* PB, int SB,
+                       const double* gtg, double l1, double l2, float* Cs32, float* Ct32, void* Ch, float* Cinv,
+                       double* gpartC, int32_t* nan_flag, void* stream);
 
 /* Sum the K1 partials over the splits in fixed order into fp64, component-major: out[t*ld + i]. */
 int scrna_nmf_reduce_rows(const float* part, int nsplit, int g, int kp, double* out, int64_t ld,

@@ -54,6 +54,12 @@ _SIGNATURES = {
     "scrna_nmf_h_shadow": [c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                            c_ptr],
     "scrna_f16_inexact": [c_ptr, c_i64, c_ptr, c_ptr],
+    "scrna_nmf_h_groups": [c_i64],
+    "scrna_nmf_step_groups": [c_i64],
+    "scrna_nmf_gstep_mu": [c_ptr, c_int, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_i64,
+                           c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_ptr, c_int, c_ptr, c_int, c_ptr, c_ptr],
+    "scrna_nmf_cstep_mu": [c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr, c_int, c_ptr, c_dbl, c_dbl, c_ptr,
+                           c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_f16_panel_rows": [c_i64],
     "scrna_f16_panel_elems": [c_i64, c_i64],
     "scrna_narrow_f32_f16": [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr],
@@ -119,10 +125,11 @@ _VALUE_RETURNING = {"scrna_abi_version", "scrna_nmf_xht_splits", "scrna_nmf_wtx_
                     "scrna_nmf_tc_shadow_elems", "scrna_bjacobi_blocks", "scrna_bjacobi_splits",
                     "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems", "scrna_kta_blocks",
                     "scrna_nmf_h_supported", "scrna_nmf_h_nb", "scrna_nmf_h_shadow_elems", "scrna_nmf_wtx_h_splits",
-                    "scrna_f16_panel_rows", "scrna_f16_panel_elems"}
+                    "scrna_f16_panel_rows", "scrna_f16_panel_elems", "scrna_nmf_h_groups", "scrna_nmf_step_groups"}
 
 
-_RETURNS_I64 = {"scrna_nmf_tc_shadow_elems", "scrna_nmf_h_shadow_elems", "scrna_f16_panel_rows", "scrna_f16_panel_elems", "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems"}
+_RETURNS_I64 = {"scrna_nmf_tc_shadow_elems", "scrna_nmf_h_shadow_elems", "scrna_f16_panel_rows", "scrna_f16_panel_elems",
+                "scrna_nmf_h_groups", "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems"}
 
 
 class ScrnaError(RuntimeError):

@@ -14,11 +14,13 @@
 // x (11 significant bits) times an fp16 part (11 bits) is exact in the fp32 accumulator, so the only rounding
 // is the accumulation itself -- identical in kind to an fp32 FMA chain.  Two parts carry 22 significant bits of
 // the factor (what the 3xTF32 sweep's [hi | lo] factor split carries; the default), three carry 33.  fp16's
-// narrow exponent range is what the per-component scale is for: s_t = 2^e with ||F[:, t]||_2 * s_t in
-// [2^12, 2^13) (from the Gram diagonal the epilogue has just produced), so no part can overflow and the absolute
-// representation error of an entry is at most 2^-25 / s_t <= 2^-37 ||F[:, t]||_2.  tcgen05.mma.kind::f16 does
-// not accept mixed f16 x bf16 operands (measured: illegal instruction, tools/microbench/f16_probe.cu), hence
-// fp16 parts and not a bf16 split.
+// narrow exponent range is what the scale is for: per component and per GROUP of 128 factor rows,
+// s = 2^e with max|F| * s in [2^13, 2^14) over the group, so no part can overflow and the absolute
+// representation error of an entry is at most 2^-25 / s <= 2^-38 of the group's largest entry.  The scale is
+// local to the 128 rows an epilogue CTA has just written (no reduction over the whole factor, the shadow is
+// emitted by the update kernel itself) and coincides with the accumulator drain period below, where it is
+// undone.  tcgen05.mma.kind::f16 does not accept mixed f16 x bf16 operands (measured: illegal instruction,
+// tools/microbench/f16_probe.cu), hence fp16 parts and not a bf16 split.
 //
 // Storage ("panel-major").  X16 is kept as panels of 256 columns: element (i, j) at
 //      ((j / 256) * rows_pad + i) * 256 + j % 256,      rows_pad = rows rounded up to 64, padding zero,
@@ -35,9 +37,10 @@
 //   B (shared memory, K-major, no swizzle): the factor rows in the canonical layout [(r/8)][n < NB][r%8];
 //   D (tensor memory): lane l of D_m = output column j0 + 128 m + l; column n = part n / KQ of component n % KQ.
 // The tensor core truncates its fp32 accumulator at every accumulation (see nmf_sweep_tc.cu; measured here:
-// a relative bias of ~1.6e-7 per MMA of the chain), so the accumulators are drained every `drain` stages
-// (256 rows) into fp32 running totals held in REGISTERS (one output column per thread and m); two accumulator
-// sets alternate in tensor memory, so the MMA stream never waits for a drain.
+// a relative bias of ~1.6e-7 per MMA of the chain), so the accumulators are drained every 128 rows (one scale
+// group: the drain multiplies by the group's 2^-e, exact) into fp32 running totals held in REGISTERS (one output
+// column per thread and m); two accumulator sets alternate in tensor memory, so the MMA stream never waits for
+// a drain.
 //
 // Pipeline (192 threads, one CTA per SM, a stage = 64 rows: 64 KB of X at CM = 4):
 //      warp 4 lane 0 : TMA producer (NBOX tensor boxes + one bulk copy of the factor block per stage);
@@ -56,7 +59,8 @@
 namespace scrna {
 
 constexpr int H_THREADS = 192;  // 4 drain warps + producer + MMA issuer
-constexpr int H_ALIGN = 64;     // row spans, panels and operand shadows are padded to this many rows
+constexpr int H_ALIGN = 128;    // row spans, panels and operand shadows are padded to this many rows
+constexpr int H_GROUP = 128;    // rows sharing one fp16 scale per component = rows between two accumulator drains
 constexpr int H_SR = 64;        // rows per pipeline stage = TMA box height = four K = 16 MMA steps
 constexpr int H_PANEL = 256;    // columns per storage panel
 
@@ -105,7 +109,7 @@ template <int KQ, int PARTS>
 __global__ void __launch_bounds__(H_THREADS, 1)
 wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int rows_pad, int64_t ncols,
              const __half* __restrict__ Fh, const float* __restrict__ inv_scale, float* __restrict__ part, int64_t ldc,
-             int rows_per_split, int drain, int flags, const NmfCtrl* __restrict__ ctrl) {
+             int rows_per_split, int flags, const NmfCtrl* __restrict__ ctrl) {
   using Cfg = HCfg<KQ, PARTS>;
   constexpr int NB = Cfg::NB, CM = Cfg::CM, NS = Cfg::NS, NACC = Cfg::NACC;
   if (ctrl_done(ctrl)) return;
@@ -125,6 +129,7 @@ wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int rows_pad, int6
   int r_end = r_begin + rows_per_split;
   if (r_end > g) r_end = g;
   const int nstages = r_end > r_begin ? (r_end - r_begin + H_SR - 1) / H_SR : 0;
+  constexpr int drain = H_GROUP / H_SR;   // stages per drain period
   const int nperiods = (nstages + drain - 1) / drain;
 
   if (tid == 0) {
@@ -219,6 +224,8 @@ wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int rows_pad, int6
       for (int t = 0; t < KQ; ++t) tot[m][t] = 0.f;
     for (int p = 0; p < nperiods; ++p) {
       const int buf = p % NACC;
+      // the period's rows are one scale group of the factor shadow: 1 / scale per component
+      const float4* inv = reinterpret_cast<const float4*>(inv_scale + ((int64_t)(r_begin / H_GROUP) + p) * KQ);
       mbar_wait(acc_full + 8 * buf, (uint32_t)((p / NACC) & 1));
       tc_fence_after();
 #pragma unroll
@@ -235,9 +242,12 @@ wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int rows_pad, int6
             tc_fence_before();
             mbar_arrive(acc_empty + 8 * buf);
           }
+          const float4 s0 = inv_scale ? __ldg(inv + t0 / 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+          const float4 s1 = inv_scale ? __ldg(inv + t0 / 4 + 1) : make_float4(1.f, 1.f, 1.f, 1.f);
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-          for (int t = 0; t < 8; ++t)  // smallest parts first
-            tot[m][t0 + t] += PARTS == 3 ? (c[t] + b[t]) + a[t] : b[t] + a[t];
+          for (int t = 0; t < 8; ++t)  // smallest parts first; unscale (a power of two: exact) and accumulate
+            tot[m][t0 + t] = fmaf(PARTS == 3 ? (c[t] + b[t]) + a[t] : b[t] + a[t], sc[t], tot[m][t0 + t]);
         }
       }
     }
@@ -247,7 +257,7 @@ wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int rows_pad, int6
       if (col0 + m * 128 + tid < ncols) {
 #pragma unroll
         for (int t = 0; t < KQ; ++t)
-          out[(int64_t)t * ldc + m * 128] = tot[m][t] * (inv_scale ? __ldg(inv_scale + t) : 1.f);
+          out[(int64_t)t * ldc + m * 128] = tot[m][t];
       }
     }
   }
@@ -261,23 +271,36 @@ wtx_h_kernel(const __grid_constant__ CUtensorMap xmap, int g, int rows_pad, int6
 }
 
 // ---- operand shadow ---------------------------------------------------------------------------------------
-// CTAs [0, row_ctas): finish the per-component scale from the Gram diagonal (sum over `nblk` block partials in
-// fixed order -- every CTA computes the same numbers) and split the factor into its three fp16 parts, K-major
-// canonical layout out[((r/8) * NB + n) * 8 + r%8], n = part * KQ + t; rows padded to 64.  A thread owns one
-// (8-row group, component) pair: it reads 64 contiguous bytes of the master and writes three 16-byte vectors,
+// CTAs [0, groups): one 128-row scale group each.  Per component the group's largest |entry| fixes the scale
+// 2^e with max * 2^e in [2^13, 2^14) -- local to the group, so no reduction over the whole factor is needed and
+// small-magnitude stretches of a factor keep their relative accuracy -- then the rows are split into fp16 parts,
+// K-major canonical layout out[((r/8) * NB + n) * 8 + r%8], n = part * KQ + t; inv_scale[group * KQ + t] = 2^-e.
+// A thread owns (8-row group, component) items: 64 contiguous bytes of the master in, 16-byte vectors out,
 // consecutive threads writing consecutive vectors.
-// CTAs [row_ctas, ...): the k x k Gram itself (one warp per entry), i.e. gram_final_kernel folded into the same
-// launch so that the iteration does not grow by a kernel.
+// CTAs [groups, ...): optionally the k x k Gram finish (one warp per entry; gram_final_kernel folded into the same
+// launch so that an iteration does not grow by a kernel).
 constexpr int HS_THREADS = 256;
+__device__ __forceinline__ float h_group_scale(double mx, float* inv) {
+  // mx * scale in [2^13, 2^14): every entry of the group is below 2^14, far inside fp16's range
+  double sc = 1.0;
+  if (mx > 0.0 && mx < 1e300) {
+    int e;
+    frexp(mx, &e);  // mx = m * 2^e, m in [0.5, 1)
+    if (e < -100) e = -100;  // keep 2^e and 2^-e inside fp32 (entries below 2^-100 lose relative accuracy only)
+    sc = ldexp(1.0, 14 - e);
+  }
+  *inv = (float)(1.0 / sc);
+  return (float)sc;
+}
+
 __global__ void __launch_bounds__(HS_THREADS)
-h_shadow_kernel(const double* __restrict__ F64, int64_t ld, int64_t rows, int64_t rows_pad, int k, int kq, int nb,
-                int parts,
+h_shadow_kernel(const double* __restrict__ F64, int64_t ld, int64_t rows, int k, int kq, int nb, int parts,
                 const double* __restrict__ gpart, int nblk, int kp, double* __restrict__ gram_out,
-                __half* __restrict__ out, float* __restrict__ inv_scale, int row_ctas, const NmfCtrl* __restrict__ ctrl) {
+                __half* __restrict__ out, float* __restrict__ inv_scale, int groups, const NmfCtrl* __restrict__ ctrl) {
   if (ctrl_done(ctrl)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if ((int)blockIdx.x >= row_ctas) {
-    const int o = ((int)blockIdx.x - row_ctas) * (HS_THREADS >> 5) + warp;
+  if ((int)blockIdx.x >= groups) {
+    const int o = ((int)blockIdx.x - groups) * (HS_THREADS >> 5) + warp;
     if (o >= kp * kp || gram_out == nullptr) return;
     const int a = o / kp, b = o - a * kp;
     double s = 0.0;
@@ -287,47 +310,52 @@ h_shadow_kernel(const double* __restrict__ F64, int64_t ld, int64_t rows, int64_
     if (lane == 0) gram_out[o] = s;
     return;
   }
-  __shared__ double sscale[SCRNA_MAX_K];
-  for (int t = warp; t < k; t += HS_THREADS >> 5) {
-    double s = 0.0;
-    for (int p = lane; p < nblk; p += 32) s += gpart[(int64_t)p * kp * kp + t * kp + t];
-    s = warp_sum(s);
-    if (lane == 0) {
-      // ||F[:, t]||_2 * scale in [2^12, 2^13): no entry can exceed 2^13, far inside fp16's range
-      double sc = 1.0;
-      if (s > 0.0 && s < 1e300) {
-        int e;
-        frexp(sqrt(s), &e);  // sqrt(s) = m * 2^e, m in [0.5, 1)
-        sc = ldexp(1.0, 13 - e);
-      }
-      sscale[t] = sc;
-      if (blockIdx.x == 0) inv_scale[t] = (float)(1.0 / sc);
-    }
-  }
-  if (blockIdx.x == 0)
-    for (int t = k + tid; t < kq; t += HS_THREADS) inv_scale[t] = 1.f;
-  __syncthreads();
-  const int64_t item = (int64_t)blockIdx.x * HS_THREADS + tid;  // (row group, component), component fastest
-  const int64_t rg = item / kq;
-  const int t = (int)(item - rg * kq);
-  if (rg >= (rows_pad >> 3)) return;
-  union Pack { uint4 v; __half h[8]; } p1, p2, p3;
-  const double sc = t < k ? sscale[t] : 0.0;
+  __shared__ double smax[16][SCRNA_MAX_K];
+  __shared__ float sscale[SCRNA_MAX_K];
+  const int64_t r0 = (int64_t)blockIdx.x * H_GROUP;
+  // pass 1: per (8-row group, component) maxima
+  for (int item = tid; item < 16 * kq; item += HS_THREADS) {
+    const int rg = item / kq, t = item - rg * kq;
+    double mx = 0.0;
+    if (t < k)
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int64_t r = rg * 8 + e;
-    double v = (r < rows && t < k) ? F64[(int64_t)t * ld + r] * sc : 0.0;
-    p1.h[e] = __double2half(v);
-    v -= (double)__half2float(p1.h[e]);
-    p2.h[e] = __double2half(v);
-    v -= (double)__half2float(p2.h[e]);
-    p3.h[e] = __double2half(v);
+      for (int e = 0; e < 8; ++e) {
+        const int64_t r = r0 + rg * 8 + e;
+        if (r < rows) mx = fmax(mx, fabs(F64[(int64_t)t * ld + r]));
+      }
+    smax[rg][t] = mx;
   }
-  uint4* base = reinterpret_cast<uint4*>(out) + rg * nb;
-  base[t] = p1.v;
-  base[kq + t] = p2.v;
-  if (parts == 3) base[2 * kq + t] = p3.v;
-  if (parts * kq + t < nb) base[parts * kq + t] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  for (int t = tid; t < kq; t += HS_THREADS) {
+    double mx = 0.0;
+#pragma unroll
+    for (int rg = 0; rg < 16; ++rg) mx = fmax(mx, smax[rg][t]);
+    float inv;
+    sscale[t] = h_group_scale(mx, &inv);
+    inv_scale[(int64_t)blockIdx.x * kq + t] = inv;
+  }
+  __syncthreads();
+  // pass 2: split and store
+  for (int item = tid; item < 16 * kq; item += HS_THREADS) {
+    const int rg = item / kq, t = item - rg * kq;
+    union Pack { uint4 v; __half h[8]; } p1, p2, p3;
+    const double sc = t < k ? (double)sscale[t] : 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int64_t r = r0 + rg * 8 + e;
+      double v = (r < rows && t < k) ? F64[(int64_t)t * ld + r] * sc : 0.0;
+      p1.h[e] = __double2half(v);
+      v -= (double)__half2float(p1.h[e]);
+      p2.h[e] = __double2half(v);
+      v -= (double)__half2float(p2.h[e]);
+      p3.h[e] = __double2half(v);
+    }
+    uint4* base = reinterpret_cast<uint4*>(out) + ((r0 >> 3) + rg) * nb;
+    base[t] = p1.v;
+    base[kq + t] = p2.v;
+    if (parts == 3) base[2 * kq + t] = p3.v;
+    if (parts * kq + t < nb) base[parts * kq + t] = make_uint4(0u, 0u, 0u, 0u);
+  }
 }
 
 // inexact[0] |= 1 if any element of X is not exactly representable in fp16 (value or range)
@@ -381,7 +409,7 @@ transpose_f16_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows
 
 template <int KQ, int PARTS>
 static int wtx_h_launch(const __half* X, int64_t rows_pad, int g, int64_t ncols, const __half* Fh, const float* inv_scale,
-                        float* part, int64_t ldc, int nsplit, int rps, int drain, int flags, const NmfCtrl* ctrl,
+                        float* part, int64_t ldc, int nsplit, int rps, int flags, const NmfCtrl* ctrl,
                         cudaStream_t st) {
   using Cfg = HCfg<KQ, PARTS>;
   CUtensorMap xmap;
@@ -398,7 +426,7 @@ static int wtx_h_launch(const __half* X, int64_t rows_pad, int g, int64_t ncols,
   }
   dim3 grid((unsigned)ceil_div(ncols, Cfg::COLS), (unsigned)nsplit);
   wtx_h_kernel<KQ, PARTS><<<grid, H_THREADS, Cfg::SMEM_BYTES, st>>>(xmap, g, (int)rows_pad, ncols, Fh, inv_scale, part, ldc,
-                                                                   rps, drain, flags, ctrl);
+                                                                   rps, flags, ctrl);
   return last_launch_status();
 }
 
@@ -441,6 +469,8 @@ extern "C" int64_t scrna_nmf_h_shadow_elems(int64_t rows, int kq, int parts) {
   return ceil_div(rows, H_ALIGN) * H_ALIGN * (int64_t)h_nb(kq, parts);
 }
 
+extern "C" int64_t scrna_nmf_h_groups(int64_t rows) { return rows > 0 ? ceil_div(rows, H_GROUP) : SCRNA_ERR_BADARG; }
+
 extern "C" int64_t scrna_f16_panel_rows(int64_t rows) { return rows > 0 ? ceil_div(rows, H_ALIGN) * H_ALIGN : SCRNA_ERR_BADARG; }
 
 extern "C" int64_t scrna_f16_panel_elems(int64_t rows, int64_t cols) {
@@ -480,17 +510,15 @@ extern "C" int scrna_nmf_wtx_partial_h(const void* X16, int64_t rows_pad, int g,
     return SCRNA_ERR_BADARG;
   const int rps = h_rows_per_split(g, nsplit);
   if ((int64_t)rps * (nsplit - 1) >= g && nsplit > 1) return SCRNA_ERR_BADARG;  // an empty span
-  int drain = (flags >> 8) & 0xffff;  // tuning override of the drain period (stages of 64 rows)
-  if (drain <= 0) drain = 4;          // 256 rows
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const NmfCtrl* c = reinterpret_cast<const NmfCtrl*>(ctrl);
   const __half* Xh = reinterpret_cast<const __half*>(X16);
   const __half* F = reinterpret_cast<const __half*>(Fh);
   if (parts == 2) {
-    SCRNA_DISPATCH_H(kq, return (wtx_h_launch<KQ, 2>(Xh, rows_pad, g, ncols, F, inv_scale, part, ldc, nsplit, rps, drain,
+    SCRNA_DISPATCH_H(kq, return (wtx_h_launch<KQ, 2>(Xh, rows_pad, g, ncols, F, inv_scale, part, ldc, nsplit, rps,
                                                      flags & 0xff, c, st)));
   } else {
-    SCRNA_DISPATCH_H(kq, return (wtx_h_launch<KQ, 3>(Xh, rows_pad, g, ncols, F, inv_scale, part, ldc, nsplit, rps, drain,
+    SCRNA_DISPATCH_H(kq, return (wtx_h_launch<KQ, 3>(Xh, rows_pad, g, ncols, F, inv_scale, part, ldc, nsplit, rps,
                                                      flags & 0xff, c, st)));
   }
   return SCRNA_ERR_UNSUPPORTED;
@@ -499,15 +527,14 @@ extern "C" int scrna_nmf_wtx_partial_h(const void* X16, int64_t rows_pad, int g,
 extern "C" int scrna_nmf_h_shadow(const double* F64, int64_t ld, int64_t rows, int k, int kq, int parts,
                                   const double* gram_parts, int nblk, int kp, double* gram_out, void* Fh,
                                   float* inv_scale, const scrna_nmf_ctrl_t* ctrl, void* stream) {
-  if (!F64 || !Fh || !inv_scale || !gram_parts || rows <= 0 || k <= 0 || k > kq || !scrna_nmf_h_supported(kq) ||
-      nblk <= 0 || kp < k || (parts != 2 && parts != 3))
+  if (!F64 || !Fh || !inv_scale || rows <= 0 || k <= 0 || k > kq || !scrna_nmf_h_supported(kq) ||
+      (gram_out && (!gram_parts || nblk <= 0 || kp < k)) || (parts != 2 && parts != 3))
     return SCRNA_ERR_BADARG;
-  const int64_t rows_pad = ceil_div(rows, H_ALIGN) * H_ALIGN;
-  const int row_ctas = (int)ceil_div((rows_pad >> 3) * kq, HS_THREADS);
+  const int groups = (int)ceil_div(rows, H_GROUP);
   const int gram_ctas = gram_out ? (int)ceil_div((int64_t)kp * kp, HS_THREADS >> 5) : 0;
-  h_shadow_kernel<<<row_ctas + gram_ctas, HS_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      F64, ld, rows, rows_pad, k, kq, h_nb(kq, parts), parts, gram_parts, nblk, kp, gram_out,
-      reinterpret_cast<__half*>(Fh), inv_scale, row_ctas, reinterpret_cast<const NmfCtrl*>(ctrl));
+  h_shadow_kernel<<<groups + gram_ctas, HS_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      F64, ld, rows, k, kq, h_nb(kq, parts), parts, gram_parts, nblk, kp, gram_out, reinterpret_cast<__half*>(Fh),
+      inv_scale, groups, reinterpret_cast<const NmfCtrl*>(ctrl));
   return last_launch_status();
 }
 

@@ -90,6 +90,19 @@ class CudaKernels:
     def wtx_h_splits(self, g, ncols, kq, parts):
         return _lib.call("scrna_nmf_wtx_h_splits", g, ncols, kq, parts)
 
+    def h_groups(self, rows):
+        return _lib.call("scrna_nmf_h_groups", rows)
+
+    def gstep_mu(self, peers, nranks, rank, off, g, ldg, k, kq, nb, parts, l1, l2, PA, SA, gpartC, groupsC, nan_flag):
+        """Fused gene half step of the MU iteration (nmf_step.cu); `off`: dict of arena byte offsets."""
+        self._call("scrna_nmf_gstep_mu", peers, nranks, rank, off["xch"], off["sync"], off["G64"], off["Gs32"], off["Gh"],
+                   off["Ginv"], off["gpart"], off["gtg"], g, ldg, k, kq, nb, parts, float(l1), float(l2), PA, SA,
+                   gpartC, groupsC, nan_flag, self._s())
+
+    def cstep_mu(self, C64, ldn, n, k, kq, nb, parts, PB, SB, gtg, l1, l2, Cs32, Ct32, Ch, Cinv, gpartC, nan_flag):
+        self._call("scrna_nmf_cstep_mu", C64, ldn, n, k, kq, nb, parts, PB, SB, gtg, float(l1), float(l2), Cs32, Ct32,
+                   Ch, Cinv, gpartC, nan_flag, self._s())
+
     def panel_rows(self, rows):
         return _lib.call("scrna_f16_panel_rows", rows)
 

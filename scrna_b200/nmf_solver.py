@@ -177,6 +177,37 @@ class TorchDistComm:
     def all_reduce(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
 
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+    def symmetric_arena(self, nbytes, device):
+        """(zeroed uint8 tensor of nbytes in torch symmetric memory, [base address of every rank's copy in THIS rank's
+        address space]) -- or None when the backend has no peer-mapped memory (gloo, no P2P): the caller then keeps
+        the NCCL all-reduce path.  Collective: every rank of the group calls it with the same size."""
+        if os.environ.get("SCRNA_B200_P2P", "1") == "0" or device.type != "cuda":
+            return None
+        try:
+            if self.dist.get_backend(self.group) != "nccl":
+                return None
+            import torch
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else self.dist.group.WORLD
+            arena = symm.empty(int(nbytes), dtype=torch.uint8, device=device)
+            hdl = symm.rendezvous(arena, group)
+            arena.zero_()
+            torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != self.world:
+                return None
+            self._symm_handles = getattr(self, "_symm_handles", []) + [hdl]
+            return arena, ptrs
+        except Exception as e:   # no symmetric memory on this build / topology: NCCL path
+            import sys
+            sys.stderr.write("scrna_b200: symmetric memory unavailable (%s: %s); using the NCCL all-reduce path\n"
+                             % (type(e).__name__, e))
+            return None
+
     def gather_cols(self, local, bounds, n_total):
         """Every rank contributes `local` (r x n_local, the columns bounds[rank]); returns the full r x n_total
         tensor on every rank (zero-padded sum: payloads here are the small factors, not X)."""
@@ -266,18 +297,27 @@ class NmfSolver:
             self.XT = XT          # a resident transposed copy built by another solver on the same X
         else:
             self.XT = X.transposed(kernels, half=self.half) if transpose_copy else None
-        self.G64 = t.zeros((kp, ldg), dtype=f64, device=dev)
-        self.Gs32 = t.zeros((g, kp), dtype=f32, device=dev)
+        self.h_parts = hp = int(os.environ.get("SCRNA_B200_H_PARTS", H_PARTS))
+        self.arena = None
+        if self.half and hasattr(kernels, "gstep_mu"):
+            self._build_arena(g, kp, ldg, hp)     # gene-side state in ONE allocation that peers can map
+        else:
+            self.G64 = t.zeros((kp, ldg), dtype=f64, device=dev)
+            self.Gs32 = t.zeros((g, kp), dtype=f32, device=dev)
         self.C64 = t.zeros((kp, ldn), dtype=f64, device=dev)
         self.Cs32 = t.zeros((n, kp), dtype=f32, device=dev)
         self.Ct32 = t.zeros((kp, ldn), dtype=f32, device=dev)
-        self.Gtc = self.Ctc = self.Gh = self.Ch = self.Ginv = self.Cinv = None
-        self.h_parts = hp = int(os.environ.get("SCRNA_B200_H_PARTS", H_PARTS))
+        self.Gtc = self.Ctc = self.Ch = self.Cinv = None
+        if not self.half:
+            self.Gh = self.Ginv = None
         if self.half:
-            self.Gh = t.zeros(kernels.h_shadow_elems(g, kp, hp), dtype=t.float16, device=dev)
+            if self.arena is None:
+                self.Gh = t.zeros(kernels.h_shadow_elems(g, kp, hp), dtype=t.float16, device=dev)
+                self.Ginv = t.ones(kernels.h_groups(g) * kp, dtype=f32, device=dev)
             self.Ch = t.zeros(kernels.h_shadow_elems(n, kp, hp), dtype=t.float16, device=dev)
-            self.Ginv = t.ones(kp, dtype=f32, device=dev)
-            self.Cinv = t.ones(kp, dtype=f32, device=dev)
+            self.Cinv = t.ones(kernels.h_groups(n) * kp, dtype=f32, device=dev)
+            self.groupsC = int(kernels.h_groups(n))
+            self.gpartC_grp = t.zeros(self.groupsC * kp * kp, dtype=f64, device=dev)
             self.SA = int(os.environ.get("SCRNA_B200_TC_SA", 0)) or kernels.wtx_h_splits(n, self.gcols, kp, hp)
             self.PA = t.zeros((self.SA, kp, ldg), dtype=f32, device=dev)
             self.SB = int(os.environ.get("SCRNA_B200_TC_SB", 0)) or kernels.wtx_h_splits(g, X.ncols, kp, hp)
@@ -302,7 +342,8 @@ class NmfSolver:
         self.R_cct = self.R[kp * ldg: kp * ldg + kp * kp]
         self.R_scal = self.R[kp * ldg + kp * kp:]
         self.NB = t.zeros((kp, ldn), dtype=f64, device=dev)
-        self.gtg = t.zeros(kp * kp, dtype=f64, device=dev)
+        if self.arena is None:
+            self.gtg = t.zeros(kp * kp, dtype=f64, device=dev)
         self.gram_part = t.zeros(kernels.gram_blocks() * kp * kp, dtype=f64, device=dev)
         self.nblkG = kernels.update_blocks(g)
         self.nblkC = kernels.update_blocks(n)
@@ -317,6 +358,45 @@ class NmfSolver:
         self.fuse_reduce = True   # partial reduction + Gram fused into the update epilogues
         self._g_num_from_R = True
         self.perms = None
+
+    # ---- gene-side arena of the fused MU iteration (nmf_step.cu) -------------------------------
+    def _build_arena(self, g, kq, ldg, parts):
+        """Exchange buffer, flags and every gene-side array of the fused iteration in ONE allocation with the same
+        layout on every rank.  With a P2P-capable communicator it is torch symmetric memory: every rank maps every
+        peer's arena, and the fused gene step reads / writes the peers' copies directly over NVLink."""
+        t, kn = self.torch, self.kn
+        dev = self.X.data.device
+        groups = int(kn.h_groups(g))
+        sizes = [("xch", (kq * ldg + kq * kq) * 8), ("sync", 64 * 4), ("G64", kq * ldg * 8), ("Gs32", g * kq * 4),
+                 ("Gh", int(kn.h_shadow_elems(g, kq, parts)) * 2), ("Ginv", groups * kq * 4),
+                 ("gpart", groups * kq * kq * 8), ("gtg", kq * kq * 8)]
+        off, total = {}, 0
+        for name, nbytes in sizes:
+            off[name] = total
+            total += (nbytes + 255) // 256 * 256
+        self.p2p = False
+        arena = None
+        if self.comm is not None and getattr(self.comm, "symmetric_arena", None) is not None:
+            got = self.comm.symmetric_arena(total, dev)
+            if got is not None:
+                arena, ptrs = got
+                self.p2p = True
+        if arena is None:
+            arena = t.zeros(total, dtype=t.uint8, device=dev)
+            ptrs = [arena.data_ptr()]
+        self.arena, self.arena_off, self.groupsG = arena, off, groups
+        self.peer_ptrs = t.tensor(ptrs, dtype=t.int64, device=dev)
+
+        def view(name, dtype, shape):
+            nbytes = int(np.prod(shape)) * t.empty(0, dtype=dtype).element_size()
+            return arena[off[name]: off[name] + nbytes].view(dtype).view(*shape)
+        self.G64 = view("G64", t.float64, (kq, ldg))
+        self.Gs32 = view("Gs32", t.float32, (g, kq))
+        self.Gh = view("Gh", t.float16, (int(kn.h_shadow_elems(g, kq, parts)),))
+        self.Ginv = view("Ginv", t.float32, (groups * kq,))
+        self.Ginv.fill_(1.0)
+        self.gtg = view("gtg", t.float64, (kq * kq,))
+        self.xch = view("xch", t.float64, (kq * ldg + kq * kq,))
 
     # ---- helpers ------------------------------------------------------------------------------
     def load_G(self, G0):
@@ -555,6 +635,41 @@ class NmfSolver:
             self._allreduce_R()
 
         use_iter_end = solver == "cd"
+        # The fused step kernels (nmf_step.cu) carry the cross-GPU exchange inside the gene step (peer loads / stores on
+        # torch symmetric memory, no NCCL in the loop).  They are correct on 1, 2 and 8 GPUs (same Frobenius error to
+        # 1e-9) but measured SLOWER than the separate epilogues + one NCCL all-reduce: 1.2405 vs 1.2196 ms per
+        # iteration on one B200, 0.674 vs 0.651 ms on two, 0.2588 vs 0.2392 ms on eight (20k x 100k, k = 8;
+        # profiles/r02_fused_step_vs_nccl.md) -- two in-kernel grid + cross-GPU barriers cost more than they save at
+        # this payload (1.3 MB).  Hence opt-in: SCRNA_B200_FUSED=1.
+        fused = (solver == "mu" and self.half and self.arena is not None and update_G and update_C and first == "G"
+                 and (self.comm is None or self.p2p) and os.environ.get("SCRNA_B200_FUSED", "0") == "1")
+        self.fused = fused
+        if fused:
+            # the fused gene step sums per-group Gram partials of the cell factor: seed them with the initial C.C^T
+            self.gpartC_grp.zero_()
+            self.gpartC_grp[: self.kp * self.kp].copy_(self.R_cct)
+            nanflag = self.ctrl[3:4]
+            nb = kn.h_nb(self.kp, self.h_parts)
+            world = self.comm.world if self.comm is not None else 1
+            rank = self.comm.rank if self.comm is not None else 0
+            if self.comm is not None:
+                self.torch.cuda.synchronize()
+                self.comm.barrier()          # every rank's arena holds its initial factors before a peer touches it
+
+            def fused_iteration():
+                X = self.X
+                self._sweep_XT(None)
+                kn.gstep_mu(self.peer_ptrs, world, rank, self.arena_off, X.g, self.ldg, self.k, self.kp, nb, self.h_parts,
+                            l1_G, l2_G, self.PA, self.SA, self.gpartC_grp, self.groupsC, nanflag)
+                self._sweep_X(None)
+                kn.cstep_mu(self.C64, self.ldn, max(X.n, 1), self.k, self.kp, nb, self.h_parts, self.PB, self.SB, self.gtg,
+                            l1_C, l2_C, self.Cs32, self.Ct32, self.Ch, self.Cinv, self.gpartC_grp, nanflag)
+
+            self.step = fused_iteration
+            self._one_iteration = fused_iteration
+            self._graph = None
+            self._plan = dict(solver=solver, tol=float(tol), max_iter=max_iter)
+            return
 
         def one_iteration():
             if first == "G":

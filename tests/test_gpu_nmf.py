@@ -93,23 +93,26 @@ def test_f16_not_chosen_for_inexact_data(kernels):
 
 
 def test_update_writes_f16_operand_shadow(kernels):
-    """The epilogue's three-part fp16 shadow equals the one scrna_nmf_h_shadow builds from the master and its Gram,
-    and the parts reconstruct the master to 2^-33 of the column norm."""
+    """The epilogue's three-part fp16 shadow equals the one scrna_nmf_h_shadow builds from the master, the scales are
+    local to 128-row groups (max|entry| * 2^e in [2^13, 2^14)), and the parts reconstruct the master to 2^-38 of the
+    group's largest entry (half a unit of fp16's subnormal spacing under a scale of at least 2^13)."""
     import scrna_b200._lib as L
     torch = kernels.torch
     rng = np.random.RandomState(5)
     rows, k, kq, ld = 1001, 13, 16, 1024
     dev = torch.device("cuda")
-    F = np.zeros((kq, ld)); F[:k, :rows] = np.abs(rng.randn(k, rows)) * np.exp(4.0 * rng.randn(k, 1))
+    F = np.zeros((kq, ld))
+    F[:k, :rows] = np.abs(rng.randn(k, rows)) * np.exp(4.0 * rng.randn(k, 1)) * np.exp(3.0 * rng.randn(1, rows))
     F64 = torch.from_numpy(F).to(dev)
     N = np.zeros((kq, ld)); N[:k, :rows] = np.abs(rng.randn(k, rows)) * 10
     A = np.abs(rng.randn(40, k)); Gm = np.zeros((kq, kq)); Gm[:k, :k] = A.T @ A
     n_el = kernels.h_shadow_elems(rows, kq, 3)
     nb = kernels.h_nb(kq, 3)
+    groups = kernels.h_groups(rows)
     sh_a = torch.zeros(n_el, dtype=torch.float16, device=dev)
     sh_b = torch.full((n_el,), -1.0, dtype=torch.float16, device=dev)
-    inv_a = torch.zeros(kq, dtype=torch.float32, device=dev)
-    inv_b = torch.zeros(kq, dtype=torch.float32, device=dev)
+    inv_a = torch.zeros(groups * kq, dtype=torch.float32, device=dev)
+    inv_b = torch.zeros(groups * kq, dtype=torch.float32, device=dev)
     S32 = torch.zeros((rows, kq), dtype=torch.float32, device=dev)
     nblk = kernels.update_blocks(rows)
     viol = torch.zeros(nblk, dtype=torch.float64, device=dev)
@@ -117,7 +120,8 @@ def test_update_writes_f16_operand_shadow(kernels):
     gout = torch.zeros(kq * kq, dtype=torch.float64, device=dev)
     ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
     kernels.update(L.SOLVER_MU, F64, ld, rows, k, kq, torch.from_numpy(N).to(dev), torch.from_numpy(Gm).to(dev), 0.5, 0.1,
-                   None, 1, 0, S32, None, viol, ctrl, gram_partials=gpart, gram_out=gout, Fh=sh_a, inv_scale=inv_a, kq=kq, parts=3)
+                   None, 1, 0, S32, None, viol, ctrl, gram_partials=gpart, gram_out=gout, Fh=sh_a, inv_scale=inv_a, kq=kq,
+                   parts=3)
     torch.cuda.synchronize()
     got = F64.cpu().numpy()[:k, :rows]
     np.testing.assert_allclose(gout.cpu().numpy().reshape(kq, kq)[:k, :k], got @ got.T, rtol=1e-12)
@@ -126,12 +130,17 @@ def test_update_writes_f16_operand_shadow(kernels):
     np.testing.assert_array_equal(sh_a.cpu().numpy(), sh_b.cpu().numpy())
     np.testing.assert_array_equal(inv_a.cpu().numpy(), inv_b.cpu().numpy())
     sh = sh_b.cpu().numpy().astype(np.float64).reshape(-1, nb, 8)             # [(r/8)][n][r%8]
-    inv = inv_b.cpu().numpy().astype(np.float64)
-    assert np.all(np.isfinite(sh)) and np.abs(sh).max() <= 2.0 ** 13
+    inv = inv_b.cpu().numpy().astype(np.float64).reshape(groups, kq)
+    assert np.all(np.isfinite(sh)) and np.abs(sh).max() < 2.0 ** 14
     parts = [sh[:, p * kq:(p + 1) * kq, :].transpose(1, 0, 2).reshape(kq, -1)[:k, :rows] for p in range(3)]
-    rec = (parts[0] + parts[1] + parts[2]) * inv[:k, None]
-    assert np.max(np.abs(rec - got) / np.linalg.norm(got, axis=1, keepdims=True)) < 2.0 ** -33
-    assert np.all(sh[:, 3 * kq:, :] == 0) and np.all(sh[:, :, :].reshape(-1, nb, 8)[:, k:kq, :] == 0)
+    grp = np.arange(rows) // 128
+    rec = (parts[0] + parts[1] + parts[2]) * inv[grp, :k].T
+    gmax = np.stack([np.abs(got[:, grp == q]).max(axis=1) for q in range(groups)], axis=1)[:, grp]   # k x rows
+    assert np.max(np.abs(rec - got) / gmax) <= 2.0 ** -38
+    assert np.all(np.abs(parts[0]).reshape(k, -1) * 0 == 0)
+    lead = np.stack([np.abs(parts[0][:, grp == q]).max(axis=1) for q in range(groups)], axis=1)
+    assert np.all(lead >= 2.0 ** 13) and np.all(lead <= 2.0 ** 14)            # every group uses fp16's top binades
+    assert np.all(sh[:, 3 * kq:, :] == 0) and np.all(sh.reshape(-1, nb, 8)[:, k:kq, :] == 0)
 
 
 @pytest.mark.parametrize("exact_x", [True, False])
