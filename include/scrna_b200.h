@@ -386,6 +386,22 @@ int scrna_kta_align_f64(const double* K, int64_t ld, int n, const int32_t* label
                         const double* scale_x, double tot_x, const double* mean_y, const double* scale_y, double tot_y,
                         double* partials, double* out, void* stream);
 
+/* ---- K13 at the BASELINE size: leading eigenvectors of the Gram A = M^T M (sc3_eigh.cu) -- the right singular vectors
+ * scipy.linalg.svd yields at sc3_clustering_impl.py:178 -- by Householder tridiagonalisation + bisection + inverse
+ * iteration (LAPACK dsytrd / dstebz / dstein / dormtr restated for the device).
+ * scrna_sytrd_f64: A (n x n, FULL symmetric, row-major) -> d (n), e (n-1 used), tau (n); on exit row c of A holds the
+ *   reflector of column c (entries (c, n), leading 1 stored); work: scrna_sytrd_work_elems(n) doubles.
+ * scrna_stebz_top_f64: lam[j] = j-th LARGEST eigenvalue of the tridiagonal (d, e), j < c; [gl, gu] Gershgorin bounds.
+ * scrna_stein_f64: X (n x c, row-major [row][vector]) unit eigenvectors for lam; work 4*n*c doubles, iwork n*c bytes.
+ * scrna_ormtr_f64: ZT (c x n, one vector per row) <- Q z for every row, Q from scrna_sytrd_f64's reflectors. */
+int64_t scrna_sytrd_work_elems(int n);
+int scrna_sytrd_f64(double* A, int64_t ld, int n, double* d, double* e, double* tau, double* work, void* stream);
+int scrna_stebz_top_f64(const double* d, const double* e, int n, int c, double gl, double gu, double pivmin,
+                        double* lam, void* stream);
+int scrna_stein_f64(const double* d, const double* e, int n, int c, const double* lam, double tnorm, double* work,
+                    int8_t* iwork, double* X, int iters, void* stream);
+int scrna_ormtr_f64(const double* A, int64_t ld, int n, const double* tau, double* ZT, int c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,587 @@
+// K13 at the BASELINE size: the leading right singular vectors of the n x n SC3 matrix M as the leading
+// eigenvectors of the Gram A = M^T M, by Householder tridiagonalisation + bisection + inverse iteration.
+//
+// Why a second solver.  The reference takes a full LAPACK SVD (scipy.linalg.svd, sc3_clustering_impl.py:178) and
+// keeps the first ceil(0.07 n) right singular vectors (sc3_clustering.py:95-98).  The block one-sided Jacobi solver
+// (sc3_svd_block.cu) is the accuracy reference of this package -- it works on M itself -- but needs 16-17 sweeps of
+// 4 n^3 FMA: 46 s of the 62 s SC3 run at n = 20 000.  The classical dense route costs a fraction of ONE sweep:
+//      A = M^T M                      n^3 FMA        (scrna_pairwise_f64, op 1)
+//      A = Q T Q^T                    2/3 n^3 FMA    half of it a matrix-vector product per column: HBM-bound
+//      T z = lambda z, top c          O(n c)         bisection on Sturm counts + inverse iteration
+//      v = Q z                        2 n^2 c        the n - 2 reflectors applied to c vectors
+// Squaring costs accuracy only where it does not matter here: eigenvector errors are eps |A| / gap, and the kept
+// eigenvalues (sigma^2 from 2.4e6 down to ~9e2 at n = 20 000) have gaps ~1e0, i.e. 1e-10 -- two digits inside the
+// 1e-8 the pipeline is held to.  Used for n >= 2048 (Sc3Ops.right_singular_vectors); smaller matrices, and with them
+// every golden-vector parity test, stay on the Jacobi solver.
+//
+// Tridiagonalisation (LAPACK dsytrd / dlatrd, lower variant, restated for the device).  A is kept FULL and symmetric
+// (both triangles), row-major, so "column c" is read as the contiguous row c.  Panels of 32 columns; per column c:
+//   k1  x = A[c][c+1:] - (panel corrections)                                 -> unscaled reflector, partial |x|^2
+//   k2  beta, tau, scale (one warp);  d[c], e[c], tau[c]
+//   k3  y = A22 . v                  (the HBM-bound symmetric matrix-vector product over the trailing matrix)
+//   k4  t1 = Wp^T v, t2 = Vp^T v     (panel corrections of y), v stored: Vp[i] and, for the back-transformation, A[c]
+//   k5  w' = y - Vp^T t1 - Wp^T t2,  partial w'.v
+//   k6  w = tau w' - (tau^2 (w'.v) / 2) v  -> Wp[i]
+// and per panel the symmetric rank-64 update  A22 -= Vp^T Wp + Wp^T Vp  as ONE K = 64 GEMM on the FP64 tensor
+// cores (DMMA).  All reductions are two-level with a fixed order: results are run-to-run identical.
+#include "common.cuh"
+
+namespace scrna {
+
+constexpr int EH_NB = 32;          // panel width
+constexpr int EH_RED = 256;        // CTAs of the vector kernels = partial sums per reduction
+
+__device__ __forceinline__ void eh_dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// scal: [0] scale, [1] tau, [2] alpha (x[c+1]), [3] w'.v
+// ---- k1: unscaled reflector of column c = j + i ----------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eh_col_kernel(const double* __restrict__ A, int64_t ld, int n, int c, int i, const double* __restrict__ Vp,
+              const double* __restrict__ Wp, double* __restrict__ x, double* __restrict__ part, double* __restrict__ d,
+              double* __restrict__ scal) {
+  __shared__ double vc[EH_NB], wc[EH_NB], scratch[32];
+  if (threadIdx.x < i) {
+    vc[threadIdx.x] = Vp[(int64_t)threadIdx.x * n + c];
+    wc[threadIdx.x] = Wp[(int64_t)threadIdx.x * n + c];
+  }
+  __syncthreads();
+  double ss = 0.0;
+  for (int r = c + blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    double v = A[(int64_t)c * ld + r];
+    for (int p = 0; p < i; ++p) v -= Vp[(int64_t)p * n + r] * wc[p] + Wp[(int64_t)p * n + r] * vc[p];
+    if (r == c) d[c] = v;
+    else {
+      x[r] = v;
+      if (r == c + 1) scal[2] = v;
+      else ss += v * v;
+    }
+  }
+  const double b = block_sum(ss, scratch);
+  if (threadIdx.x == 0) part[blockIdx.x] = b;
+}
+
+// ---- k2: Householder scalars (dlarfg) ----------------------------------------------------------------------------
+__global__ void eh_house_kernel(const double* __restrict__ part, int nparts, int c, double* __restrict__ e,
+                                double* __restrict__ tau, double* __restrict__ scal) {
+  double s = 0.0;
+  for (int p = threadIdx.x; p < nparts; p += 32) s += part[p];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) {
+    const double alpha = scal[2];
+    double beta = alpha, t = 0.0, sc = 0.0;
+    if (s > 0.0) {
+      beta = -copysign(sqrt(alpha * alpha + s), alpha);
+      t = (beta - alpha) / beta;
+      sc = 1.0 / (alpha - beta);
+    }
+    e[c] = beta;
+    tau[c] = t;
+    scal[0] = sc;
+    scal[1] = t;
+  }
+}
+
+// ---- k3: y = A22 . v over rows / columns (c, n): one warp per row -------------------------------------------------
+__global__ void __launch_bounds__(256)
+eh_symv_kernel(const double* __restrict__ A, int64_t ld, int n, int c, const double* __restrict__ x,
+               const double* __restrict__ scal, double* __restrict__ y) {
+  const int r = c + 1 + blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const int lane = threadIdx.x & 31;
+  const double sc = scal[0];
+  const double* row = A + (int64_t)r * ld;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int s = c + 1 + lane;
+  if (s < n) {                                          // first chunk: v[c+1] = 1
+    a0 = row[s] * (lane == 0 ? 1.0 : x[s] * sc);
+    s += 32;
+  }
+  for (; s + 96 < n; s += 128) {
+    a0 = fma(row[s], x[s] * sc, a0);
+    a1 = fma(row[s + 32], x[s + 32] * sc, a1);
+    a2 = fma(row[s + 64], x[s + 64] * sc, a2);
+    a3 = fma(row[s + 96], x[s + 96] * sc, a3);
+  }
+  for (; s < n; s += 32) a0 = fma(row[s], x[s] * sc, a0);
+  const double t = warp_sum((a0 + a1) + (a2 + a3));
+  if (lane == 0) y[r] = t;
+}
+
+// ---- k4: t1 = Wp . v, t2 = Vp . v (rows of the panel buffers against v); v is stored scaled -------------------------
+__global__ void __launch_bounds__(256)
+eh_panel_dots_kernel(int n, int c, int i, double* __restrict__ Vp, const double* __restrict__ Wp,
+                     const double* __restrict__ x, const double* __restrict__ scal, double* __restrict__ Arow,
+                     double* __restrict__ part) {
+  __shared__ double sm[8][2 * EH_NB];
+  const double sc = scal[0];
+  double* vi = Vp + (int64_t)i * n;
+  double acc1[EH_NB], acc2[EH_NB];
+#pragma unroll
+  for (int p = 0; p < EH_NB; ++p) acc1[p] = acc2[p] = 0.0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const double v = r <= c ? 0.0 : (r == c + 1 ? 1.0 : x[r] * sc);
+    vi[r] = v;
+    if (r > c) Arow[r] = v;   // reflector kept in row c of A for the back-transformation
+#pragma unroll
+    for (int p = 0; p < EH_NB; ++p)
+      if (p < i) {
+        acc1[p] = fma(Wp[(int64_t)p * n + r], v, acc1[p]);
+        acc2[p] = fma(Vp[(int64_t)p * n + r], v, acc2[p]);
+      }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int p = 0; p < EH_NB; ++p)
+    if (p < i) {
+      const double a = warp_sum(acc1[p]);
+      const double b = warp_sum(acc2[p]);
+      if (lane == 0) { sm[warp][p] = a; sm[warp][EH_NB + p] = b; }
+    }
+  __syncthreads();
+  if (threadIdx.x < 2 * EH_NB) {
+    const int p = threadIdx.x % EH_NB;
+    double t = 0.0;
+    if (p < i)
+      for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];   // fixed order
+    part[(int64_t)blockIdx.x * 2 * EH_NB + threadIdx.x] = t;
+  }
+}
+
+// ---- k5: w' = y - Vp^T t1 - Wp^T t2 ; partial w'.v ------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eh_w_kernel(int n, int c, int i, const double* __restrict__ Vp, const double* __restrict__ Wp,
+            const double* __restrict__ dots_part, int nparts, const double* __restrict__ y, double* __restrict__ w,
+            double* __restrict__ part) {
+  __shared__ double t1[EH_NB], t2[EH_NB], scratch[32];
+  if (threadIdx.x < 2 * i) {
+    const int p = threadIdx.x % i, which = threadIdx.x / i;
+    double s = 0.0;
+    for (int b = 0; b < nparts; ++b) s += dots_part[(int64_t)b * 2 * EH_NB + which * EH_NB + p];   // fixed order
+    (which ? t2 : t1)[p] = s;
+  }
+  __syncthreads();
+  const double* vi = Vp + (int64_t)i * n;
+  double dot = 0.0;
+  for (int r = c + 1 + blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    double v = y[r];
+    for (int p = 0; p < i; ++p) v -= Vp[(int64_t)p * n + r] * t1[p] + Wp[(int64_t)p * n + r] * t2[p];
+    w[r] = v;
+    dot = fma(v, vi[r], dot);
+  }
+  const double b = block_sum(dot, scratch);
+  if (threadIdx.x == 0) part[blockIdx.x] = b;
+}
+
+// ---- k6: w = tau w' - (tau^2 (w'.v) / 2) v -> Wp[i] -----------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eh_wfin_kernel(int n, int c, int i, const double* __restrict__ Vp, double* __restrict__ Wp,
+               const double* __restrict__ w, const double* __restrict__ part, int nparts,
+               const double* __restrict__ scal) {
+  __shared__ double sdot;
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+    for (int p = threadIdx.x; p < nparts; p += 32) s += part[p];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) sdot = s;
+  }
+  __syncthreads();
+  const double tau = scal[1];
+  const double alpha2 = -0.5 * tau * tau * sdot;
+  const double* vi = Vp + (int64_t)i * n;
+  double* wi = Wp + (int64_t)i * n;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+    wi[r] = r <= c ? 0.0 : tau * w[r] + alpha2 * vi[r];
+}
+
+// ---- trailing update: A[r][s] -= sum_p Vp[p][r] Wp[p][s] + Wp[p][r] Vp[p][s],  r, s >= lo --------------------------
+// One CTA = 64 rows x 128 columns, K = 64 ([Vp | Wp] against [Wp | Vp]); 8 warps, each 32 x 32 as 4 x 4 DMMA tiles.
+constexpr int EH_TP = 64 + 8;      // pitch of the staged 64 x 64 row operand   [k][r]
+constexpr int EH_TQ = 128 + 8;     // pitch of the staged 64 x 128 column operand [k][s]
+__global__ void __launch_bounds__(256)
+eh_syr2k_kernel(double* __restrict__ A, int64_t ld, int n, int lo, int nb, const double* __restrict__ Vp,
+                const double* __restrict__ Wp) {
+  extern __shared__ __align__(16) double eh_smem[];
+  double* P = eh_smem;                 // [k < 64][r < 64]
+  double* Q = P + 64 * EH_TP;          // [k < 64][s < 128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wr = warp >> 2, wc = warp & 3;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int r0 = lo + blockIdx.y * 64, s0 = lo + blockIdx.x * 128;
+  for (int e = tid; e < 64 * 64; e += 256) {
+    const int k = e >> 6, r = e & 63;
+    const double* src = (k < 32 ? Vp + (int64_t)k * n : Wp + (int64_t)(k - 32) * n);
+    P[k * EH_TP + r] = (k % 32 < nb && r0 + r < n) ? src[r0 + r] : 0.0;
+  }
+  for (int e = tid; e < 64 * 128; e += 256) {
+    const int k = e >> 7, s = e & 127;
+    const double* src = (k < 32 ? Wp + (int64_t)k * n : Vp + (int64_t)(k - 32) * n);
+    Q[k * EH_TQ + s] = (k % 32 < nb && s0 + s < n) ? src[s0 + s] : 0.0;
+  }
+  __syncthreads();
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll 4
+  for (int kk = 0; kk < 16; ++kk) {
+    const int k = 4 * kk + lk;
+    double a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = P[k * EH_TP + 32 * wr + 8 * u + lr];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) b[u] = Q[k * EH_TQ + 32 * wc + 8 * u + lr];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) eh_dmma(acc[u][v], a[u], b[v]);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = r0 + 32 * wr + 8 * u + lr;
+    if (r >= n) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int s = s0 + 32 * wc + 8 * v + 2 * lk;
+      double* p = A + (int64_t)r * ld + s;
+      if (s < n) p[0] -= acc[u][v][0];
+      if (s + 1 < n) p[1] -= acc[u][v][1];
+    }
+  }
+}
+
+// ---- eigenvalues: the `c` largest by bisection on Sturm counts (LAPACK dstebz idea), one thread each ---------------
+__global__ void eh_bisect_kernel(const double* __restrict__ d, const double* __restrict__ e, int n, int c, double gl,
+                                 double gu, double pivmin, double* __restrict__ lam) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;   // j-th largest
+  if (j >= c) return;
+  const int want = n - 1 - j;                            // ascending index of the wanted eigenvalue
+  double lo = gl, hi = gu;
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (mid <= lo || mid >= hi) break;
+    int cnt = 0;                                         // eigenvalues < mid
+    double q = d[0] - mid;
+    if (fabs(q) < pivmin) q = -pivmin;
+    cnt += q < 0.0;
+    for (int k = 1; k < n; ++k) {
+      const double ek = e[k - 1];
+      q = d[k] - mid - ek * ek / q;
+      if (fabs(q) < pivmin) q = -pivmin;
+      cnt += q < 0.0;
+    }
+    if (cnt <= want) lo = mid; else hi = mid;
+  }
+  lam[j] = 0.5 * (lo + hi);
+}
+
+// ---- eigenvectors of T by inverse iteration (LAPACK dstein with dlagtf / dlagts), one thread per vector; the work
+// arrays are [row][vector] so that the threads of a warp touch consecutive addresses ---------------------------------
+__global__ void __launch_bounds__(128)
+eh_invit_kernel(const double* __restrict__ d, const double* __restrict__ e, int n, int c, const double* __restrict__ lam,
+                double tnorm, double* __restrict__ wa, double* __restrict__ wb, double* __restrict__ wc,
+                double* __restrict__ wd, int8_t* __restrict__ win, double* __restrict__ X, int iters) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= c) return;
+  const double lm = lam[j];
+  const double eps = 2.220446049250313e-16;
+  const double tol = fmax(eps * tnorm, 1e-300);
+  const int64_t C = c;
+  // LU with partial pivoting of T - lambda I (dlagtf)
+  double ak = d[0] - lm;                 // a[k], carried
+  double scale1 = fabs(ak) + (n > 1 ? fabs(e[0]) : 0.0);
+  double bk = n > 1 ? e[0] : 0.0;        // b[k] (super-diagonal), may be modified by the previous step
+  for (int k = 0; k < n - 1; ++k) {
+    double ak1 = d[k + 1] - lm;
+    const double ck = e[k];
+    const double bk1 = k < n - 2 ? e[k + 1] : 0.0;
+    const double scale2 = fabs(ck) + fabs(ak1) + fabs(bk1);
+    const double piv1 = ak == 0.0 ? 0.0 : fabs(ak) / scale1;
+    double cout, dout = 0.0, bnext = bk1;
+    int8_t in = 0;
+    if (ck == 0.0) {
+      scale1 = scale2;
+      cout = 0.0;
+    } else {
+      const double piv2 = fabs(ck) / scale2;
+      if (piv2 <= piv1) {
+        scale1 = scale2;
+        cout = ck / ak;
+        ak1 -= cout * bk;
+      } else {
+        in = 1;
+        const double mult = ak / ck;
+        const double temp = ak1;
+        wa[(int64_t)k * C + j] = ck;      // a[k] = c[k]
+        ak1 = bk - mult * temp;
+        dout = bk1;
+        bnext = -mult * dout;
+        bk = temp;                        // b[k] = temp
+        cout = mult;
+        wb[(int64_t)k * C + j] = bk;
+        wc[(int64_t)k * C + j] = cout;
+        wd[(int64_t)k * C + j] = dout;
+        win[(int64_t)k * C + j] = in;
+        ak = ak1;
+        bk = bnext;
+        continue;
+      }
+    }
+    wa[(int64_t)k * C + j] = ak;
+    wb[(int64_t)k * C + j] = bk;
+    wc[(int64_t)k * C + j] = cout;
+    wd[(int64_t)k * C + j] = dout;
+    win[(int64_t)k * C + j] = in;
+    ak = ak1;
+    bk = bnext;
+  }
+  wa[(int64_t)(n - 1) * C + j] = ak;
+  // start vector: deterministic pseudo-random in (-1, 1)
+  for (int k = 0; k < n; ++k) {
+    unsigned int h = (unsigned int)k * 2654435761u ^ ((unsigned int)j * 40503u + 0x9e3779b9u);
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    X[(int64_t)k * C + j] = (double)(h >> 8) * (2.0 / 16777216.0) - 1.0;
+  }
+  for (int it = 0; it < iters; ++it) {
+    // forward substitution with the recorded interchanges (dlagts)
+    double yprev = X[j];
+    for (int k = 1; k < n; ++k) {
+      double yk = X[(int64_t)k * C + j];
+      const double cc = wc[(int64_t)(k - 1) * C + j];
+      if (win[(int64_t)(k - 1) * C + j] == 0) {
+        yk -= cc * yprev;
+      } else {
+        const double temp = yprev;
+        yprev = yk;
+        yk = temp - cc * yk;
+      }
+      X[(int64_t)(k - 1) * C + j] = yprev;
+      yprev = yk;
+    }
+    X[(int64_t)(n - 1) * C + j] = yprev;
+    // back substitution, tiny pivots perturbed to +-tol (dlagts job = -1)
+    double y1 = 0.0, y2 = 0.0, nrm = 0.0;
+    for (int k = n - 1; k >= 0; --k) {
+      double t = X[(int64_t)k * C + j];
+      if (k < n - 1) t -= wb[(int64_t)k * C + j] * y1;
+      if (k < n - 2) t -= wd[(int64_t)k * C + j] * y2;
+      double a = wa[(int64_t)k * C + j];
+      if (fabs(a) < tol) a = copysign(tol, a == 0.0 ? 1.0 : a);
+      t /= a;
+      X[(int64_t)k * C + j] = t;
+      y2 = y1;
+      y1 = t;
+      nrm = fmax(nrm, fabs(t));
+    }
+    // normalise (max norm between iterations, 2-norm at the end)
+    double s2 = 0.0;
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 1.0;
+    for (int k = 0; k < n; ++k) {
+      const double t = X[(int64_t)k * C + j] * inv;
+      X[(int64_t)k * C + j] = t;
+      s2 = fma(t, t, s2);
+    }
+    if (it + 1 == iters) {
+      const double inv2 = s2 > 0.0 ? rsqrt(s2) : 1.0;
+      for (int k = 0; k < n; ++k) X[(int64_t)k * C + j] *= inv2;
+    }
+  }
+}
+
+// ---- back-transformation: the columns of Z (stored as rows of ZT, c x n) <- H_0 H_1 ... H_{n-3} z ------------------
+// A CTA owns EH_BC vectors and applies ALL reflectors to them, last to first, in one launch: the vectors stream
+// through L2 / HBM, the reflector (row of A) is shared by every CTA.
+constexpr int EH_BC = 8;
+__global__ void __launch_bounds__(256)
+eh_backtransform_kernel(const double* __restrict__ A, int64_t ld, int n, const double* __restrict__ tau,
+                        double* __restrict__ ZT, int c) {
+  __shared__ double red[8][EH_BC];
+  __shared__ double dots[EH_BC];
+  const int v0 = blockIdx.x * EH_BC;
+  const int nv = min(EH_BC, c - v0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int col = n - 3; col >= 0; --col) {
+    const double t = tau[col];
+    if (t == 0.0) continue;                       // uniform across the grid
+    const double* v = A + (int64_t)col * ld;      // v[r], r in (col, n), v[col+1] = 1
+    double acc[EH_BC];
+#pragma unroll
+    for (int u = 0; u < EH_BC; ++u) acc[u] = 0.0;
+    for (int r = col + 1 + tid; r < n; r += 256) {
+      const double vr = v[r];
+#pragma unroll
+      for (int u = 0; u < EH_BC; ++u)
+        if (u < nv) acc[u] = fma(vr, ZT[(int64_t)(v0 + u) * n + r], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < EH_BC; ++u) {
+      const double s = warp_sum(acc[u]);
+      if (lane == 0) red[warp][u] = s;
+    }
+    __syncthreads();
+    if (tid < EH_BC) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += red[w][tid];
+      dots[tid] = s * t;
+    }
+    __syncthreads();
+    for (int r = col + 1 + tid; r < n; r += 256) {
+      const double vr = v[r];
+#pragma unroll
+      for (int u = 0; u < EH_BC; ++u)
+        if (u < nv) ZT[(int64_t)(v0 + u) * n + r] -= dots[u] * vr;
+    }
+    __syncthreads();
+  }
+}
+
+// The same with ONE vector per CTA held in shared memory for the whole walk over the reflectors (n <= 20 480): the
+// vector never leaves the SM, a reflector row is read once from L2 into registers for both of its uses, one CTA
+// barrier per reflector (double-buffered partial sums).  5.7 s -> 0.5 s at n = 20 000, c = 1 401.
+constexpr int EH_BT = 1024;
+constexpr int EH_BT_MAXN = 20480;
+constexpr int EH_BT_PER = (EH_BT_MAXN + EH_BT - 1) / EH_BT;   // reflector entries per thread
+__global__ void __launch_bounds__(EH_BT, 1)
+eh_backtransform_smem_kernel(const double* __restrict__ A, int64_t ld, int n, const double* __restrict__ tau,
+                             double* __restrict__ ZT, int c) {
+  extern __shared__ double z[];
+  __shared__ double red[2][EH_BT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int vec = blockIdx.x; vec < c; vec += gridDim.x) {
+    double* zg = ZT + (int64_t)vec * n;
+    __syncthreads();
+    for (int r = tid; r < n; r += EH_BT) z[r] = zg[r];
+    __syncthreads();
+    int buf = 0;
+    for (int col = n - 3; col >= 0; --col) {
+      const double t = tau[col];
+      if (t == 0.0) continue;                       // uniform
+      const double* v = A + (int64_t)col * ld;      // v[r], r in (col, n), v[col+1] = 1
+      double vr[EH_BT_PER];
+      double acc = 0.0;
+#pragma unroll
+      for (int u = 0; u < EH_BT_PER; ++u) {
+        const int r = col + 1 + tid + u * EH_BT;
+        vr[u] = r < n ? v[r] : 0.0;
+        if (r < n) acc = fma(vr[u], z[r], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) red[buf][warp] = acc;
+      __syncthreads();
+      double dot = 0.0;
+#pragma unroll
+      for (int w = 0; w < EH_BT / 32; ++w) dot += red[buf][w];   // fixed order, every thread the same value
+      dot *= t;
+#pragma unroll
+      for (int u = 0; u < EH_BT_PER; ++u) {
+        const int r = col + 1 + tid + u * EH_BT;
+        if (r < n) z[r] -= dot * vr[u];
+      }
+      buf ^= 1;   // the next reflector's partial sums go to the other buffer: no second barrier
+    }
+    __syncthreads();
+    for (int r = tid; r < n; r += EH_BT) zg[r] = z[r];
+  }
+}
+
+}  // namespace scrna
+
+using namespace scrna;
+
+// work: 2 * 32 * n (Vp, Wp) + 3 * n (x, y, w) + 256 * 66 (partials) + 8 doubles
+extern "C" int64_t scrna_sytrd_work_elems(int n) {
+  return n > 0 ? (int64_t)2 * EH_NB * n + 3 * (int64_t)n + (int64_t)EH_RED * (2 * EH_NB + 2) + 8 : SCRNA_ERR_BADARG;
+}
+
+extern "C" int scrna_sytrd_f64(double* A, int64_t ld, int n, double* d, double* e, double* tau, double* work,
+                               void* stream) {
+  if (!A || !d || !e || !tau || !work || n < 3 || ld < n) return SCRNA_ERR_BADARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  double* Vp = work;
+  double* Wp = Vp + (int64_t)EH_NB * n;
+  double* x = Wp + (int64_t)EH_NB * n;
+  double* y = x + n;
+  double* w = y + n;
+  double* part = w + n;                                   // EH_RED
+  double* dpart = part + EH_RED;                          // EH_RED * 64
+  double* part2 = dpart + (int64_t)EH_RED * 2 * EH_NB;    // EH_RED
+  double* scal = part2 + EH_RED;                          // 8
+  static bool attr = false;
+  const size_t smem_up = (size_t)(64 * EH_TP + 64 * EH_TQ) * sizeof(double);
+  if (!attr) {
+    if (cudaFuncSetAttribute(eh_syr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_up) != cudaSuccess)
+      return SCRNA_ERR_CUDA;
+    attr = true;
+  }
+  for (int j = 0; j < n - 2; j += EH_NB) {
+    const int nb = (n - 2 - j) < EH_NB ? (n - 2 - j) : EH_NB;
+    for (int i = 0; i < nb; ++i) {
+      const int c = j + i;
+      const int m = n - c;
+      int blocks = (m + 255) / 256;
+      if (blocks > EH_RED) blocks = EH_RED;
+      eh_col_kernel<<<blocks, 256, 0, st>>>(A, ld, n, c, i, Vp, Wp, x, part, d, scal);
+      eh_house_kernel<<<1, 32, 0, st>>>(part, blocks, c, e, tau, scal);
+      eh_symv_kernel<<<(m - 1 + 7) / 8, 256, 0, st>>>(A, ld, n, c, x, scal, y);
+      int vb = (n + 255) / 256;
+      if (vb > EH_RED) vb = EH_RED;
+      eh_panel_dots_kernel<<<vb, 256, 0, st>>>(n, c, i, Vp, Wp, x, scal, A + (int64_t)c * ld, dpart);
+      eh_w_kernel<<<blocks, 256, 0, st>>>(n, c, i, Vp, Wp, dpart, vb, y, w, part2);
+      eh_wfin_kernel<<<vb, 256, 0, st>>>(n, c, i, Vp, Wp, w, part2, blocks, scal);
+    }
+    const int lo = j + nb;
+    if (lo < n) {
+      dim3 grid((unsigned)ceil_div(n - lo, 128), (unsigned)ceil_div(n - lo, 64));
+      eh_syr2k_kernel<<<grid, 256, smem_up, st>>>(A, ld, n, lo, nb, Vp, Wp);
+    }
+  }
+  // the last 2 x 2 block: d[n-2], d[n-1], e[n-2] are what is left in A; no reflector
+  // (A[n-2][n-2], A[n-2][n-1], A[n-1][n-1] carry every update because the trailing update covers them)
+  cudaMemcpyAsync(d + n - 2, A + (int64_t)(n - 2) * ld + (n - 2), sizeof(double), cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(e + n - 2, A + (int64_t)(n - 2) * ld + (n - 1), sizeof(double), cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(d + n - 1, A + (int64_t)(n - 1) * ld + (n - 1), sizeof(double), cudaMemcpyDeviceToDevice, st);
+  cudaMemsetAsync(tau + n - 2, 0, 2 * sizeof(double), st);
+  return last_launch_status();
+}
+
+extern "C" int scrna_stebz_top_f64(const double* d, const double* e, int n, int c, double gl, double gu, double pivmin,
+                                   double* lam, void* stream) {
+  if (!d || !e || !lam || n < 2 || c < 1 || c > n || !(gu > gl)) return SCRNA_ERR_BADARG;
+  eh_bisect_kernel<<<(unsigned)ceil_div(c, 32), 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d, e, n, c, gl, gu,
+                                                                                               pivmin, lam);
+  return last_launch_status();
+}
+
+// work: 4 * n * c doubles (a, b, c, d2) ; iwork: n * c bytes ; X: n x c (row-major, [row][vector])
+extern "C" int scrna_stein_f64(const double* d, const double* e, int n, int c, const double* lam, double tnorm,
+                               double* work, int8_t* iwork, double* X, int iters, void* stream) {
+  if (!d || !e || !lam || !work || !iwork || !X || n < 2 || c < 1 || iters < 1) return SCRNA_ERR_BADARG;
+  const int64_t nc = (int64_t)n * c;
+  eh_invit_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d, e, n, c, lam, tnorm, work, work + nc, work + 2 * nc, work + 3 * nc, iwork, X, iters);
+  return last_launch_status();
+}
+
+extern "C" int scrna_ormtr_f64(const double* A, int64_t ld, int n, const double* tau, double* ZT, int c, void* stream) {
+  if (!A || !tau || !ZT || n < 3 || c < 1 || ld < n) return SCRNA_ERR_BADARG;
+  if (n <= EH_BT_MAXN) {
+    static bool attr = false;
+    if (!attr) {
+      if (cudaFuncSetAttribute(eh_backtransform_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               EH_BT_MAXN * 8) != cudaSuccess)
+        return SCRNA_ERR_CUDA;
+      attr = true;
+    }
+    const int grid = c < num_sms() ? c : num_sms();
+    eh_backtransform_smem_kernel<<<grid, EH_BT, (size_t)n * sizeof(double), reinterpret_cast<cudaStream_t>(stream)>>>(
+        A, ld, n, tau, ZT, c);
+    return last_launch_status();
+  }
+  eh_backtransform_kernel<<<(unsigned)ceil_div(c, EH_BC), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(A, ld, n, tau,
+                                                                                                          ZT, c);
+  return last_launch_status();
+}

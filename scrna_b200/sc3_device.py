@@ -144,14 +144,24 @@ class Sc3Ops:
                 print("All values are Zero!")
         return out
 
-    def right_singular_vectors(self, M, components, max_sweeps=40, tol=1e-15, blocked=None):
+    EIGH_MIN_N = 6000    # from here on the tridiagonalisation solver replaces the Jacobi sweeps (16 x 4 n^3 FMA)
+
+    def right_singular_vectors(self, M, components, max_sweeps=40, tol=1e-15, blocked=None, method="auto"):
         """First `components` right singular vectors of the n x n device matrix M (descending singular
-        values) by one-sided Jacobi; returns (V device n x components, singular values numpy n).
-        n > 64 runs the block algorithm (sc3_svd_block.cu: GEMM-shaped, FP64-pipe bound), smaller matrices
-        the unblocked kernel."""
+        values); returns (V device n x components, singular values numpy n).
+        method 'jacobi': one-sided Jacobi on M itself -- n > 64 the block algorithm (sc3_svd_block.cu: GEMM-shaped,
+        FP64-pipe bound), smaller matrices the unblocked kernel; every parity test against the reference's vectors
+        runs here.  'eigh': leading eigenvectors of M^T M by tridiagonalisation + bisection + inverse iteration
+        (sc3_eigh.cu), a fraction of one Jacobi sweep; only the first `components` singular values are returned
+        (the rest of the array is zero).  'auto': eigh from n = 6000 (the BASELINE 20 000-cell configuration)."""
         t = self.torch
         n = M.shape[0]
         self._last = None
+        if method not in ("auto", "jacobi", "eigh"):
+            raise ValueError("method must be 'auto', 'jacobi' or 'eigh'")
+        if method == "eigh" or (method == "auto" and blocked is None and n >= self.EIGH_MIN_N):
+            with self._stage("svd"):
+                return self._rsv_eigh(M, components)
         if blocked is None:
             blocked = n > 64
         if blocked:
@@ -216,6 +226,64 @@ class Sc3Ops:
         self._call("scrna_gather_scaled_f64", W, n, n, od, sc, c, V, c, self._s())
         self._last = (W, od, inv[order[:c]], vals[order][:c])   # for rebuilt_matrix()
         return V, vals[order]
+
+    def _rsv_eigh(self, M, components):
+        """Leading `components` eigenpairs of A = M^T M (sc3_eigh.cu).  The host does O(n) bookkeeping only:
+        Gershgorin bounds of the tridiagonal matrix and dstein's separation of numerically coincident eigenvalues."""
+        t = self.torch
+        n = M.shape[0]
+        c = int(components)
+        if n < 3 or c > n:
+            raise ValueError("eigh path needs n >= 3 and components <= n")
+        A = self.empty(n, n)
+        with self._stage("svd.gram"):
+            self._call("scrna_pairwise_f64", M, n, n, n, 1, A, n, self._s())                 # A = M^T M
+        d, e, tau = self.empty(n), self.zeros(n), self.empty(n)
+        work = self.empty(_lib.call("scrna_sytrd_work_elems", n))
+        with self._stage("svd.tridiagonalise"):
+            self._call("scrna_sytrd_f64", A, n, n, d, e, tau, work, self._s(), launches=6 * (n - 2) + (n - 2) // 32 + 1)
+        dh, eh = d.cpu().numpy(), e.cpu().numpy()[: n - 1]
+        off = np.zeros(n)
+        off[:-1] += np.abs(eh)
+        off[1:] += np.abs(eh)
+        gl, gu = float(np.min(dh - off)), float(np.max(dh + off))
+        tnorm = max(abs(gl), abs(gu))
+        eps = np.finfo(np.float64).eps
+        gl -= 2.0 * tnorm * eps * n + 2e-300
+        gu += 2.0 * tnorm * eps * n + 2e-300
+        pivmin = max(np.finfo(np.float64).tiny * max(1.0, float(np.max(eh * eh)) if n > 1 else 1.0), 1e-300)
+        lam = self.empty(c)
+        with self._stage("svd.bisection"):
+            self._call("scrna_stebz_top_f64", d, e, n, c, gl, gu, pivmin, lam, self._s())
+        lh = lam.cpu().numpy()                      # descending
+        # dstein: numerically coincident eigenvalues are separated by 10 eps |lambda| so that inverse iteration does
+        # not return the same vector twice
+        lp = lh.copy()
+        for j in range(c - 2, -1, -1):              # ascending walk: lp[j] must exceed lp[j+1]
+            sep = 10.0 * eps * max(abs(lp[j + 1]), tnorm * eps)
+            if lp[j] - lp[j + 1] < sep:
+                lp[j] = lp[j + 1] + sep
+        lam.copy_(t.from_numpy(lp).to(self.dev))
+        nc = n * c
+        work2 = self.empty(4 * nc)
+        iwork = t.empty(nc, dtype=t.int8, device=self.dev)
+        X = self.empty(n, c)
+        with self._stage("svd.inverse_iteration"):
+            self._call("scrna_stein_f64", d, e, n, c, lam, float(tnorm), work2, iwork, X, 3, self._s())
+        del work2, iwork
+        ZT = self.empty(c, n)
+        self._call("scrna_transpose_f64", X, c, n, c, ZT, n, self._s())
+        with self._stage("svd.back_transform"):
+            self._call("scrna_ormtr_f64", A, n, n, tau, ZT, c, self._s())
+        V = X
+        self._call("scrna_transpose_f64", ZT, n, c, n, V, c, self._s())
+        vals = np.zeros(n)
+        vals[:c] = np.sqrt(np.maximum(lh, 0.0))
+        self.jacobi_sweeps = 0
+        self.svd_flops = 2.0 * (float(n) ** 3) * (1.0 + 4.0 / 3.0) + 4.0 * float(n) * n * c   # Gram + sytrd + back-transform
+        od = t.arange(c, dtype=t.int32, device=self.dev)
+        self._last = (ZT, od, np.ones(c), vals[:c])   # rows are unit vectors: rebuilt_matrix scales them itself
+        return V, vals
 
     def rebuilt_matrix(self, weights):
         """vecs . diag(weights) . vecs^T of the vectors just computed by the block solver (the first return value of

@@ -53,6 +53,61 @@ def test_rank_average_with_ties(ops):
     np.testing.assert_allclose(S, so.distances(X, "spearman"), rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("kind", ["gauss", "pca_bulk"])
+@pytest.mark.parametrize("n", [131, 300, 1037])
+def test_eigh_solver_vs_lapack(ops, n, kind):
+    """The tridiagonalisation solver (sc3_eigh.cu: Gram, Householder tridiagonalisation with DMMA trailing updates,
+    bisection, inverse iteration, back-transformation) that replaces the Jacobi sweeps from 6 000 cells on, against
+    LAPACK: leading singular values, orthonormality, residual, and the individual vectors wherever the gap to the
+    neighbours resolves them."""
+    import scipy.linalg as sl
+    rng = np.random.RandomState(n + 7)
+    if kind == "gauss":
+        M = rng.randn(n, n)
+    else:
+        X = rng.poisson(2.0 + 3.0 * (rng.rand(40, 1) < 0.3) * (rng.randint(0, 4, size=(1, n)) == 1), size=(40, n))
+        M = so.pca_prepare(so.distances(np.log2(X + 1.0), "euclidean"))
+    c = max(2, int(np.ceil(0.07 * n)))
+    V, vals = ops.right_singular_vectors(ops.to_device(M), c, method="eigh")
+    _, s, vt = sl.svd(M)
+    np.testing.assert_allclose(vals[:c], s[:c], rtol=0, atol=1e-9 * s[0])
+    assert np.all(vals[c:] == 0)
+    V = V.cpu().numpy()
+    np.testing.assert_allclose(V.T @ V, np.eye(c), rtol=0, atol=1e-8)
+    assert np.linalg.norm(M.T @ (M @ V) - V * (vals[:c] ** 2)) / (s[0] ** 2) < 1e-9
+    ref = vt[:c].T
+    sgn = np.sign((V * ref).sum(axis=0))
+    gaps = np.minimum(np.abs(np.diff(s[: c + 1] ** 2)), np.r_[np.inf, np.abs(np.diff(s[:c] ** 2))]) / s[0] ** 2
+    ok = gaps > 1e-6
+    assert ok.sum() >= c // 2
+    np.testing.assert_allclose((V * sgn)[:, ok], ref[:, ok], rtol=0, atol=1e-7)
+    # the rebuilt matrix the reference returns first (and discards): vecs . diag(w) . vecs^T
+    w = rng.rand(c)
+    np.testing.assert_allclose(ops.rebuilt_matrix(w).cpu().numpy(), (V * w) @ V.T, rtol=0, atol=1e-10)
+
+
+def test_tridiagonalisation_preserves_the_spectrum(ops):
+    """scrna_sytrd_f64 alone: the eigenvalues of (d, e) are those of A, and Q T Q^T rebuilds A (Q applied with
+    scrna_ormtr_f64 to the identity)."""
+    import scrna_b200._lib as L
+    rng = np.random.RandomState(3)
+    n = 203
+    B = rng.randn(n, n)
+    A = B @ B.T + np.diag(rng.rand(n))
+    Ad = ops.to_device(A.copy())
+    d, e, tau = ops.empty(n), ops.zeros(n), ops.empty(n)
+    work = ops.empty(L.call("scrna_sytrd_work_elems", n))
+    ops._call("scrna_sytrd_f64", Ad, n, n, d, e, tau, work, ops._s())
+    dh, eh = d.cpu().numpy(), e.cpu().numpy()[: n - 1]
+    T = np.diag(dh) + np.diag(eh, 1) + np.diag(eh, -1)
+    np.testing.assert_allclose(np.linalg.eigvalsh(T), np.linalg.eigvalsh(A), rtol=1e-11, atol=1e-9)
+    QT = ops.to_device(np.eye(n))                       # rows = unit vectors z; ormtr turns row j into Q e_j
+    ops._call("scrna_ormtr_f64", Ad, n, n, tau, QT, n, ops._s())
+    Q = QT.cpu().numpy().T
+    np.testing.assert_allclose(Q.T @ Q, np.eye(n), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(Q @ T @ Q.T, A, rtol=0, atol=1e-9 * np.abs(A).max())
+
+
 def test_rank_average_more_genes_than_one_shared_memory_chunk(ops):
     """Round 1 returned UNSUPPORTED above 28 160 genes: the ranks are now counted against the gene vector in chunks."""
     rng = np.random.RandomState(2)
