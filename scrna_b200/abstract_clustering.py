@@ -50,7 +50,13 @@ class AbstractClustering(object):
         keep_genes = np.arange(n_genes)
         for flt in (self.gene_filter_list or []):
             keep_genes = np.intersect1d(keep_genes, flt(data))   # evaluated on ALL cells, as the reference
-        sliced = data[:, keep_cells][keep_genes, :]
+        # data[:, keep_cells][keep_genes, :] as the reference, minus the fancy-index passes that select everything
+        # (two gather copies of a 3.2 GB matrix at 20 000 x 20 000); the result is always a fresh array
+        a = data if keep_cells.size == n_cells else data[:, keep_cells]
+        if keep_genes.size == n_genes:
+            sliced = a.copy() if a is data else a
+        else:
+            sliced = a[keep_genes, :]
         return self.data_transf(sliced), keep_genes, keep_cells
 
     def apply(self):

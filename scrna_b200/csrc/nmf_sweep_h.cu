@@ -15,8 +15,9 @@
 // is the accumulation itself -- identical in kind to an fp32 FMA chain.  Two parts carry 22 significant bits of
 // the factor (what the 3xTF32 sweep's [hi | lo] factor split carries; the default), three carry 33.  fp16's
 // narrow exponent range is what the scale is for: per component and per GROUP of 128 factor rows,
-// s = 2^e with max|F| * s in [2^13, 2^14) over the group, so no part can overflow and the absolute
-// representation error of an entry is at most 2^-25 / s <= 2^-38 of the group's largest entry.  The scale is
+// s = 2^e with max|F| * s in [2^13, 2^14) over the group, so no part can overflow and an entry v is
+// represented to max(2^-22 |v| (two parts; 2^-33 with three), 2^-25 / s <= 2^-38 of the group's largest entry):
+// full split precision down to 2^-16 of the group maximum, an absolute floor below.  The scale is
 // local to the 128 rows an epilogue CTA has just written (no reduction over the whole factor, the shadow is
 // emitted by the update kernel itself) and coincides with the accumulator drain period below, where it is
 // undone.  tcgen05.mma.kind::f16 does not accept mixed f16 x bf16 operands (measured: illegal instruction,

@@ -54,8 +54,9 @@ def randomized_svd_device(prod, k, seed=0, n_oversamples=10):
     n_iter = 7 if k < 0.1 * min(g, n) else 4
     transpose = g < n                      # sklearn works on M = X^T when X has more columns than rows
     xt = getattr(prod, "xt_times_full", prod.xt_times)      # global products when the cells are sharded
-    x_times = _chunked(prod.x_times, prod.k)
-    xt_times = _chunked(xt, prod.k)
+    width = getattr(prod, "k", k + n_oversamples)          # the solver's rank; wider operands go in column chunks
+    x_times = _chunked(prod.x_times, width)
+    xt_times = _chunked(xt, width)
     if transpose:
         m_times, mt_times, m_cols = xt_times, x_times, g
     else:

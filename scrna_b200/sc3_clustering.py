@@ -64,11 +64,20 @@ class SC3Clustering(AbstractClustering):
         assert self.pc_range[1] < self.num_cells
         X = self.pre_processing()
 
-        dists = [d(X, self.gene_ids[self.remain_gene_inds]) for d in self.dists_list]
+        # Between this package's OWN stage functions the n x n intermediates stay in HBM (DeviceResult) and the
+        # matrix the reference's dimred returns first -- and its only caller, this loop, discards -- is not formed;
+        # user-supplied callables get and return NumPy arrays exactly as in the reference.
+        own_dimred = bool(self.dimred_list) and all(_impl.is_own(t, _impl.transformations) for t in self.dimred_list)
+        dists = []
+        for d in self.dists_list:
+            if own_dimred and _impl.is_own(d, _impl.distances):
+                dists.append(d(X, self.gene_ids[self.remain_gene_inds], _device=True))
+            else:
+                dists.append(d(X, self.gene_ids[self.remain_gene_inds]))
         transf = []
         for d in dists:
             for t in self.dimred_list:
-                transf.append(t(d))
+                transf.append(t(d, _device=True) if own_dimred else t(d))
 
         range_inds = list(range(self.pc_range[0], self.pc_range[1] + 1))
         if self.sub_sample and len(range_inds) > 15:
@@ -118,7 +127,10 @@ class SC3Clustering(AbstractClustering):
                     cnt += 1.
         if device_acc:
             C = ops.consensus_from_counts(M, cnt)
-            consensus2 = _impl._remember(C.cpu().numpy(), C)
+            if _impl.is_own(self.consensus_clustering, _impl.consensus_clustering):
+                consensus2 = _impl.DeviceResult(C)
+            else:
+                consensus2 = _impl._remember(C.cpu().numpy(), C)
         else:
             consensus2 /= cnt
         self.cluster_labels, self.dists = self.consensus_clustering(consensus2)

@@ -114,11 +114,38 @@ def _ops():
     return default_ops()
 
 
-def distances(data, gene_ids, metric='euclidean'):
+class DeviceResult:
+    """A stage result that stays in HBM: what this package's own SC3Clustering passes between this package's own
+    stage functions (`_device=True`) instead of an n x n NumPy array -- at 20 000 cells every such array is a 3.2 GB
+    device-to-host copy the next stage would only upload again.  Never handed to user-supplied callables."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.shape = tuple(tensor.shape)
+
+    def host(self):
+        return self.tensor.cpu().numpy()
+
+
+def _device_of(x):
+    """Device tensor of a stage input: a DeviceResult, the resident twin of a remembered host array, or None."""
+    if isinstance(x, DeviceResult):
+        return x.tensor
+    return _lookup(x)
+
+
+def is_own(fn, target):
+    """True when the callable (possibly a functools.partial) is this module's `target`."""
+    return getattr(fn, "func", fn) is target
+
+
+def distances(data, gene_ids, metric='euclidean', _device=False):
     """cells x cells distance matrix of a transcripts x cells matrix (scRNA/sc3_clustering_impl.py:106-132):
     'euclidean' (bit-identical to scipy pdist), 'pearson' (1 - corrcoef), 'spearman' (1 - rank corrcoef)."""
     ops = _ops()
     D = ops.distances(np.asarray(data, dtype=np.float64), metric)
+    if _device:
+        return DeviceResult(D)
     return _remember(D.cpu().numpy(), D)
 
 
@@ -147,17 +174,20 @@ def da_nmf_distances(data, gene_ids, da_model, reject_ratio=0., metric='euclidea
     return mixture * (dist2 * scale) + (1. - mixture) * dist1
 
 
-def transformations(dm, components=5, method='pca'):
+def transformations(dm, components=5, method='pca', _device=False):
     """(cells x cells matrix rebuilt from the kept components, cells x components right singular vectors)
     of the PCA-scaled or 'spectral' distance matrix (scRNA/sc3_clustering_impl.py:135-203).  The first return
-    value is what the reference computes and its only caller discards (sc3_clustering.py:77,95)."""
+    value is what the reference computes and its only caller discards (sc3_clustering.py:77,95); this package's
+    own SC3Clustering asks for it not to be formed (`_device=True`: (None, vectors))."""
     ops = _ops()
-    dev = _lookup(dm)
+    dev = _device_of(dm)
     D = dev if dev is not None else ops.to_device(np.asarray(dm, dtype=np.float64))
     num_cells = D.shape[0]
     M = ops.transform_matrix(D, method)
     V, vals = ops.right_singular_vectors(M, components)
     vecs = V.cpu().numpy()
+    if _device:
+        return None, _remember(vecs, V)
     vals = vals / np.sqrt(np.max((1, num_cells - 1)))
     if ops._last is not None:
         rebuilt = ops.rebuilt_matrix(vals[:components]).cpu().numpy()     # n x n Gram on the device
@@ -219,7 +249,7 @@ def consensus_clustering(consensus, n_components=5):
     """(labels, cells x cells Euclidean distances between consensus rows): pdist -> complete linkage ->
     cut_tree(n_components) (scRNA/sc3_clustering_impl.py:244-260)."""
     ops = _ops()
-    dev = _lookup(consensus)
+    dev = _device_of(consensus)
     C = dev if dev is not None else ops.to_device(np.asarray(consensus, dtype=np.float64))
     labels, D, _ = ops.consensus_clustering(C, n_components)
     return labels, D.cpu().numpy()

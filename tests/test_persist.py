@@ -70,33 +70,55 @@ def test_alias_refuses_to_shadow_a_real_reference_import(monkeypatch):
         persist.reference_alias()
 
 
+OURS_WRITES_AND_READS = r"""
+import sys
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, %(root)r + "/tests")
+import numpy as np
+from test_persist import _fitted_like
+from scrna_b200 import NmfClustering_initW
+from scrna_b200.persist import save_source_model, load_source_model
+obj = _fitted_like(NmfClustering_initW)
+save_source_model(%(path)r, obj)
+assert type(obj) is NmfClustering_initW and obj.cell_filter_list == []      # the live object is untouched
+back = load_source_model(%(path)r)
+assert type(back) is NmfClustering_initW
+assert np.array_equal(back.dictionary, obj.dictionary) and np.array_equal(back.pre_processing(), obj.pp_data)
+print("OK", repr(float(obj.dictionary.sum())))
+"""
+
+OURS_READS = r"""
+import sys
+sys.path.insert(0, %(root)r)
+from scrna_b200 import NmfClustering_initW
+from scrna_b200.persist import load_source_model
+src = load_source_model(%(path)r)
+assert type(src) is NmfClustering_initW and isinstance(src, NmfClustering_initW)
+assert src.dictionary.shape == (10, 2) and src.data_matrix.shape == (2, 7) and src.num_cluster == 2
+assert src.pre_processing().shape == (10, 7)                                 # pass-through filters re-armed
+print("OK", repr(float(src.dictionary.sum())))
+"""
+
+
+def _run(script, **kw):
+    out = subprocess.run([sys.executable, "-c", script % dict(root=ROOT, **kw)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return out.stdout
+
+
 @needs_ref
 def test_model_written_here_is_read_by_the_unmodified_reference(tmp_path):
-    from scrna_b200 import NmfClustering_initW
-    from scrna_b200.persist import save_source_model, load_source_model
-    obj = _fitted_like(NmfClustering_initW)
+    # every side in its own process: the class path scRNA.* belongs to whichever package is imported there
     path = str(tmp_path / "src_c3.npz")
-    save_source_model(path, obj)
-    assert type(obj) is NmfClustering_initW and obj.cell_filter_list == []      # the live object is untouched
-    out = subprocess.run([sys.executable, "-c", REF_READS % dict(root=ROOT, path=path)], capture_output=True, text=True)
-    assert out.returncode == 0, out.stderr[-2000:]
-    assert out.stdout.startswith("OK (12, 3) (3, 9) (12, 9) 3"), out.stdout
-    assert abs(float(out.stdout.split()[-1]) - obj.dictionary.sum()) < 1e-12
-    back = load_source_model(path)
-    assert type(back) is NmfClustering_initW
-    np.testing.assert_array_equal(back.dictionary, obj.dictionary)
-    np.testing.assert_array_equal(back.pre_processing(), obj.pp_data)
+    ours = _run(OURS_WRITES_AND_READS, path=path)
+    theirs = _run(REF_READS, path=path)
+    assert theirs.startswith("OK (12, 3) (3, 9) (12, 9) 3"), theirs
+    assert abs(float(theirs.split()[-1]) - float(ours.split()[-1])) < 1e-12
 
 
 @needs_ref
 def test_model_written_by_the_reference_loads_into_our_classes(tmp_path):
-    from scrna_b200 import NmfClustering_initW
-    from scrna_b200.persist import load_source_model
     path = str(tmp_path / "ref_c2.npz")
-    out = subprocess.run([sys.executable, "-c", REF_WRITES % dict(root=ROOT, path=path)], capture_output=True, text=True)
-    assert out.returncode == 0, out.stderr[-2000:]
-    src = load_source_model(path)
-    assert type(src) is NmfClustering_initW and isinstance(src, NmfClustering_initW)
-    assert src.dictionary.shape == (10, 2) and src.data_matrix.shape == (2, 7) and src.num_cluster == 2
-    assert abs(src.dictionary.sum() - float(out.stdout.split()[-1])) < 1e-12
-    assert src.pre_processing().shape == (10, 7)                                 # pass-through filters re-armed
+    theirs = _run(REF_WRITES, path=path)
+    ours = _run(OURS_READS, path=path)
+    assert abs(float(ours.split()[-1]) - float(theirs.split()[-1])) < 1e-12
