@@ -266,6 +266,18 @@ int scrna_sum_f64(const double* v, int n, double* out, double scale, void* strea
 int scrna_transfer_mu_step(double* H64, float* H32, const double* WtX, const double* WtW, int k, int kp,
                            int64_t ncols, int64_t ldc, scrna_nmf_ctrl_t* ctrl, void* stream);
 
+/* One iteration of the transfer loop (utils.py:195-206) with the stop rule on the device.  scrna_transfer_iteration =
+ * K6 + the L1 residual of the updated H (X: fp32 row-major with ldx, or the fp16 panel layout with ldx = rows_pad when
+ * x_is_f16; n cells, ncols = n rounded up to the shard's zero padding); the caller all-reduces `out` across cell
+ * shards if there are any, then scrna_transfer_stop turns it into err = out / denom (denom = genes x all target cells), applies |err_prev - err| / err_prev <= rel_err && err_prev >= err
+ * (or ZERO_DEN, or max_iter) and sets ctrl->done / n_iter / err_last.  All kernels of later enqueued iterations return
+ * at once when ctrl->done is set: the host enqueues a batch and reads the control block once per batch. */
+int scrna_transfer_iteration(const void* X, int x_is_f16, int64_t ldx, int g, int64_t n, int64_t ncols, const float* G32,
+                             double* H64, float* H32, const double* WtX, const double* WtW, int k, int kp, int64_t ldc,
+                             double* partials, double* out, scrna_nmf_ctrl_t* ctrl, void* stream);
+int scrna_transfer_stop(const double* res, double denom, double rel_err, int max_iter, scrna_nmf_ctrl_t* ctrl,
+                        void* stream);
+
 /* labels[j] = argmax_t H64[t][j], ties -> lowest t (np.argmax; utils.py:210, nmf_clustering.py:170). */
 int scrna_argmax_cols(const double* H64, int k, int64_t ncols, int64_t ldc, int32_t* labels, void* stream);
 
@@ -349,6 +361,13 @@ int scrna_kmeans_pp(const double* X, int64_t ldx, int n, int d, const double* xs
                     const double* uniforms, int ntrials, double* closest, double* cand_dist, double* cums,
                     double* pots, int32_t* cand, int32_t* idx, double* state, double* C, int64_t ldc,
                     void* stream);
+/* Same with the first centre chosen by the caller: first = searchsorted(cdf, u0, side='right') for
+ * cdf = cumsum(full(n, 1/n)) / cumsum[-1] (numpy RandomState.choice) -- a sequential n-term sum the host evaluates once
+ * per n instead of one device thread walking it for every restart. */
+int scrna_kmeans_pp_from(const double* X, int64_t ldx, int n, int d, const double* xsq, int k, int first,
+                         const double* uniforms, int ntrials, double* closest, double* cand_dist, double* cums,
+                         double* pots, int32_t* cand, int32_t* idx, double* state, double* C, int64_t ldc,
+                         void* stream);
 int scrna_lloyd_assign(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc, int k,
                        int32_t* labels, void* stream);
 int64_t scrna_lloyd_sums_work_elems(int k, int d);
@@ -356,6 +375,13 @@ int scrna_lloyd_sums(const double* X, int64_t ldx, int n, int d, const int32_t* 
                      int64_t lds, int32_t* counts, double* work, void* stream);
 int scrna_lloyd_finish(double* Cnew, const double* Cold, int64_t ldc, int k, int d, const int32_t* counts,
                        const int32_t* labels, int32_t* labels_old, int n, double* state, void* stream);
+/* One gated Lloyd iteration: assign -> sums -> relocate -> finish, with sklearn's stop rule (_kmeans.py:700-722) on the
+ * device: state[6] = 1 (labels unchanged) / 2 (centre shift <= tol) / 3 (max_iter), state[7] = iterations done.  Once
+ * set, every kernel of a later enqueued iteration returns at once: the host enqueues batches and polls.  The host
+ * swaps Ccur / Cnxt every call; the final centres are the Cnxt of iteration state[7].  Zero state[6..7] per run. */
+int scrna_lloyd_iteration(const double* X, int64_t ldx, int n, int d, const double* Ccur, double* Cnxt, int64_t ldc,
+                          int k, int32_t* labels, int32_t* labels_old, int32_t* counts, double* celld, double* work,
+                          double* state, int max_iter, void* stream);
 int scrna_km_cell_dist(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc,
                        const int32_t* labels, double* out, void* stream);
 int scrna_km_inertia(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc,

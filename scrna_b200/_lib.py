@@ -112,10 +112,17 @@ _SIGNATURES = {
     "scrna_km_prepare": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_kmeans_pp": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_dbl, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                         c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
+    "scrna_kmeans_pp_from": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                             c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     "scrna_lloyd_assign": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_int, c_ptr, c_ptr],
     "scrna_lloyd_sums": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr],
     "scrna_lloyd_sums_work_elems": [c_int, c_int],
     "scrna_lloyd_finish": [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr],
+    "scrna_transfer_iteration": [c_ptr, c_int, c_i64, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_i64,
+                                 c_ptr, c_ptr, c_ptr, c_ptr],
+    "scrna_transfer_stop": [c_ptr, c_dbl, c_dbl, c_int, c_ptr, c_ptr],
+    "scrna_lloyd_iteration": [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                              c_ptr, c_int, c_ptr],
     "scrna_km_cell_dist": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr],
     "scrna_km_inertia": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_km_relocate": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_int, c_ptr],

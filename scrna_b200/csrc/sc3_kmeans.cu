@@ -15,7 +15,12 @@
 namespace scrna {
 
 // state block of one k-means run (device, doubles): see KM_* offsets
-enum { KM_TOL = 0, KM_POT = 1, KM_SHIFT = 2, KM_INERTIA = 3, KM_CHANGED = 4, KM_EMPTY = 5, KM_STATE = 8 };
+// KM_DONE / KM_ITERS: device-side stop rule of the Lloyd loop (scrna_lloyd_iteration): 1 = labels unchanged (strict
+// convergence), 2 = centre shift within tol, 3 = max_iter; every kernel of a gated iteration returns at once when it
+// is set, so the host enqueues iterations in batches and polls instead of reading scalars after each one.
+enum { KM_TOL = 0, KM_POT = 1, KM_SHIFT = 2, KM_INERTIA = 3, KM_CHANGED = 4, KM_EMPTY = 5, KM_DONE = 6, KM_ITERS = 7,
+       KM_STATE = 8 };
+__device__ __forceinline__ bool km_done(const double* gate) { return gate != nullptr && gate[KM_DONE] != 0.0; }
 
 // ---- prepare ---------------------------------------------------------------------------------------
 __global__ void km_colstats_kernel(const double* __restrict__ V, int64_t ldv, int n, int d,
@@ -181,10 +186,16 @@ __global__ void gather_centers_kernel(const double* __restrict__ X, int64_t ldx,
 }
 
 // ---- Lloyd ---------------------------------------------------------------------------------------
+// One warp owns ASSIGN_CW cells and sweeps the features once per block of ASSIGN_KB centres: the cell entries stay
+// in registers, every centre entry read from L1 serves all the warp's cells, and each (cell, centre) dot product is
+// accumulated per lane in feature order and then warp-reduced -- the same arithmetic, in the same order, as one dot
+// product at a time.
+constexpr int ASSIGN_CW = 2, ASSIGN_KB = 8;
 __global__ void __launch_bounds__(256)
 lloyd_assign_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const double* __restrict__ C,
-                    int64_t ldc, int k, int* __restrict__ labels) {
+                    int64_t ldc, int k, int* __restrict__ labels, const double* __restrict__ gate) {
   extern __shared__ double csq[];  // k squared centre norms
+  if (km_done(gate)) return;
   for (int j = threadIdx.x >> 5; j < k; j += (blockDim.x >> 5)) {
     double s = 0.0;
     for (int f = threadIdx.x & 31; f < d; f += 32) { const double v = C[(int64_t)j * ldc + f]; s = fma(v, v, s); }
@@ -192,20 +203,69 @@ lloyd_assign_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, con
     if ((threadIdx.x & 31) == 0) csq[j] = s;
   }
   __syncthreads();
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int i0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ASSIGN_CW;
   const int lane = threadIdx.x & 31;
-  if (i >= n) return;
-  const double* xi = X + (int64_t)i * ldx;
-  double best = 0.0;
-  int bj = 0;
-  for (int j = 0; j < k; ++j) {
-    double dot = 0.0;
-    for (int f = lane; f < d; f += 32) dot = fma(xi[f], C[(int64_t)j * ldc + f], dot);
-    dot = warp_sum(dot);
-    const double v = csq[j] - 2.0 * dot;
-    if (j == 0 || v < best) { best = v; bj = j; }
+  if (i0 >= n) return;
+  const double* xr[ASSIGN_CW];
+#pragma unroll
+  for (int c = 0; c < ASSIGN_CW; ++c) xr[c] = X + (int64_t)min(i0 + c, n - 1) * ldx;
+  double best[ASSIGN_CW];
+  int bj[ASSIGN_CW];
+#pragma unroll
+  for (int c = 0; c < ASSIGN_CW; ++c) { best[c] = 0.0; bj[c] = 0; }
+  for (int j0 = 0; j0 < k; j0 += ASSIGN_KB) {
+    const int kb = min(ASSIGN_KB, k - j0);
+    const double* cb = C + (int64_t)j0 * ldc;
+    double acc[ASSIGN_CW][ASSIGN_KB];
+#pragma unroll
+    for (int c = 0; c < ASSIGN_CW; ++c)
+#pragma unroll
+      for (int q = 0; q < ASSIGN_KB; ++q) acc[c][q] = 0.0;
+    int f = lane;
+    for (; f + 96 < d; f += 128) {   // four feature steps of every cell in flight before the first use
+      double x[4][ASSIGN_CW];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int c = 0; c < ASSIGN_CW; ++c) x[u][c] = xr[c][f + 32 * u];
+      asm volatile("" ::: "memory");   // keep the loads batched: the compiler otherwise interleaves them with their uses
+#pragma unroll
+      for (int q = 0; q < ASSIGN_KB; ++q) {
+        if (q < kb) {
+          const double* cq = cb + (int64_t)q * ldc + f;
+          const double c0 = cq[0], c1 = cq[32], c2 = cq[64], c3 = cq[96];
+#pragma unroll
+          for (int c = 0; c < ASSIGN_CW; ++c)
+            acc[c][q] = fma(x[3][c], c3, fma(x[2][c], c2, fma(x[1][c], c1, fma(x[0][c], c0, acc[c][q]))));
+        }
+      }
+    }
+    for (; f < d; f += 32) {
+#pragma unroll
+      for (int q = 0; q < ASSIGN_KB; ++q) {
+        if (q < kb) {
+          const double c0 = cb[(int64_t)q * ldc + f];
+#pragma unroll
+          for (int c = 0; c < ASSIGN_CW; ++c) acc[c][q] = fma(xr[c][f], c0, acc[c][q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < ASSIGN_KB; ++q) {
+      if (q < kb) {
+#pragma unroll
+        for (int c = 0; c < ASSIGN_CW; ++c) {
+          const double v = csq[j0 + q] - 2.0 * warp_sum(acc[c][q]);
+          if (j0 + q == 0 || v < best[c]) { best[c] = v; bj[c] = j0 + q; }
+        }
+      }
+    }
   }
-  if (lane == 0) labels[i] = bj;
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < ASSIGN_CW; ++c)
+      if (i0 + c < n) labels[i0 + c] = bj[c];
+  }
 }
 
 // sums[j][f] = sum over cells with label j; counts[j].  The cells are cut into KM_SEG fixed segments: a
@@ -215,8 +275,9 @@ lloyd_assign_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, con
 constexpr int KM_SEG = 32;
 __global__ void __launch_bounds__(128)
 lloyd_sums_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const int* __restrict__ labels, int k,
-                  double* __restrict__ psum, int* __restrict__ pcnt) {
+                  double* __restrict__ psum, int* __restrict__ pcnt, const double* __restrict__ gate) {
   extern __shared__ double sacc[];  // k x 128
+  if (km_done(gate)) return;
   const int seg = blockIdx.y, tid = threadIdx.x;
   const int f = blockIdx.x * 128 + tid;
   const int per = (n + KM_SEG - 1) / KM_SEG;
@@ -225,7 +286,28 @@ lloyd_sums_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const
   if (f < d) {
     const double* xf = X + f;
     int i = i0;
-    for (; i + 4 <= i1; i += 4) {  // four independent loads in flight, accumulation still in cell order
+    // Register double buffer: the sixteen (label, entry) pairs of the NEXT step are requested before the current
+    // sixteen are added (in cell order) into shared memory, so sixteen loads per thread stay in flight.
+    if (i + 16 <= i1) {
+      int l[16];
+      double x[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) { l[u] = labels[i + u]; x[u] = xf[(int64_t)(i + u) * ldx]; }
+      for (; i + 32 <= i1; i += 16) {
+        int ln[16];
+        double xn[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { ln[u] = labels[i + 16 + u]; xn[u] = xf[(int64_t)(i + 16 + u) * ldx]; }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) sacc[l[u] * 128 + tid] += x[u];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { l[u] = ln[u]; x[u] = xn[u]; }
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) sacc[l[u] * 128 + tid] += x[u];
+      i += 16;
+    }
+    for (; i + 4 <= i1; i += 4) {
       const int l0 = labels[i], l1 = labels[i + 1], l2 = labels[i + 2], l3 = labels[i + 3];
       const double x0 = xf[(int64_t)i * ldx], x1 = xf[(int64_t)(i + 1) * ldx], x2 = xf[(int64_t)(i + 2) * ldx],
                    x3 = xf[(int64_t)(i + 3) * ldx];
@@ -245,7 +327,9 @@ lloyd_sums_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const
 }
 
 __global__ void lloyd_sums_final_kernel(const double* __restrict__ psum, const int* __restrict__ pcnt, int k, int d,
-                                        double* __restrict__ sums, int64_t lds, int* __restrict__ counts) {
+                                        double* __restrict__ sums, int64_t lds, int* __restrict__ counts,
+                                        const double* __restrict__ gate) {
+  if (km_done(gate)) return;
   const int j = blockIdx.y;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f < d) {
@@ -265,8 +349,9 @@ __global__ void lloyd_sums_final_kernel(const double* __restrict__ psum, const i
 __global__ void __launch_bounds__(1024)
 lloyd_finish_kernel(double* __restrict__ Cnew, const double* __restrict__ Cold, int64_t ldc, int k, int d,
                     const int* __restrict__ counts, const int* __restrict__ labels, int* __restrict__ labels_old,
-                    int n, double* __restrict__ state) {
+                    int n, double* __restrict__ state, int max_iter) {
   __shared__ double scratch[32];
+  if (max_iter > 0 && state[KM_DONE] != 0.0) return;
   __shared__ int s_changed, s_amax, s_empty;
   if (threadIdx.x == 0) {
     int am = 0, ne = 0;
@@ -309,6 +394,13 @@ lloyd_finish_kernel(double* __restrict__ Cnew, const double* __restrict__ Cold, 
     state[KM_SHIFT] = tot;
     state[KM_CHANGED] = (double)s_changed;
     state[KM_EMPTY] = (double)s_empty;
+    if (max_iter > 0) {   // gated loop: the stop rule of sklearn's _kmeans_single_lloyd (_kmeans.py:700-722) on the device
+      const double it = state[KM_ITERS] + 1.0;
+      state[KM_ITERS] = it;
+      if (s_changed == 0) state[KM_DONE] = 1.0;
+      else if (tot <= state[KM_TOL]) state[KM_DONE] = 2.0;
+      else if (it >= (double)max_iter) state[KM_DONE] = 3.0;
+    }
   }
 }
 
@@ -338,8 +430,9 @@ __global__ void km_store_sum_kernel(const double* __restrict__ src, double* __re
 __global__ void __launch_bounds__(1024)
 km_relocate_kernel(const double* __restrict__ X, int64_t ldx, int n, int d, const double* __restrict__ Cold,
                    int64_t ldc, double* __restrict__ sums, int64_t lds, int* __restrict__ counts,
-                   const int* __restrict__ labels, double* __restrict__ celld, int k) {
+                   const int* __restrict__ labels, double* __restrict__ celld, int k, const double* __restrict__ gate) {
   __shared__ double bv[32];
+  if (km_done(gate)) return;
   __shared__ int bi[32];
   __shared__ int s_far, s_any;
   __shared__ double s_max;
@@ -409,17 +502,22 @@ extern "C" int scrna_km_prepare(const double* V, int64_t ldv, int n, int d, doub
   return last_launch_status();
 }
 
-extern "C" int scrna_kmeans_pp(const double* X, int64_t ldx, int n, int d, const double* xsq, int k, double u0,
-                               const double* uniforms, int ntrials, double* closest, double* cand_dist,
-                               double* cums, double* pots, int32_t* cand, int32_t* idx, double* state, double* C,
-                               int64_t ldc, void* stream) {
+__global__ void kpp_set_first_kernel(int first, int* __restrict__ idx) {
+  if (threadIdx.x == 0) idx[0] = first;
+}
+
+static int kmeans_pp_launch(const double* X, int64_t ldx, int n, int d, const double* xsq, int k, double u0, int first,
+                            const double* uniforms, int ntrials, double* closest, double* cand_dist,
+                            double* cums, double* pots, int32_t* cand, int32_t* idx, double* state, double* C,
+                            int64_t ldc, void* stream) {
   // u0: the uniform of RandomState.choice; uniforms: (k-1)*ntrials doubles on the device (the
   // uniform(size=ntrials) draws of centres 1..k-1); cand_dist: ntrials*n; cums: n; pots: ntrials
   if (!X || !xsq || (!uniforms && k > 1) || !closest || !cand_dist || !cums || !pots || !cand || !idx || !state ||
       !C || n <= 0 || d <= 0 || k <= 0 || k > n || ntrials <= 0 || ntrials > 8 || ldx < d || ldc < d)
     return SCRNA_ERR_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
-  kpp_first_kernel<<<1, 32, 0, st>>>(n, u0, idx);
+  if (first >= 0) kpp_set_first_kernel<<<1, 32, 0, st>>>(first, idx);
+  else kpp_first_kernel<<<1, 32, 0, st>>>(n, u0, idx);
   const unsigned gb = (unsigned)ceil_div(n, 8);
   kpp_dist_kernel<8><<<gb, 256, 0, st>>>(X, ldx, n, d, xsq, idx, 1, nullptr, closest);
   row_sums_kernel<<<1, 1024, 0, st>>>(closest, n, pots);
@@ -436,11 +534,31 @@ extern "C" int scrna_kmeans_pp(const double* X, int64_t ldx, int n, int d, const
   return last_launch_status();
 }
 
+extern "C" int scrna_kmeans_pp(const double* X, int64_t ldx, int n, int d, const double* xsq, int k, double u0,
+                               const double* uniforms, int ntrials, double* closest, double* cand_dist,
+                               double* cums, double* pots, int32_t* cand, int32_t* idx, double* state, double* C,
+                               int64_t ldc, void* stream) {
+  return kmeans_pp_launch(X, ldx, n, d, xsq, k, u0, -1, uniforms, ntrials, closest, cand_dist, cums, pots, cand, idx,
+                          state, C, ldc, stream);
+}
+
+// Same, with the first centre already chosen by the caller (RandomState.choice over a uniform p is a sequential
+// n-term cumulative sum; the host evaluates it once per n with the reference's own NumPy arithmetic instead of a
+// single device thread walking it for every restart).
+extern "C" int scrna_kmeans_pp_from(const double* X, int64_t ldx, int n, int d, const double* xsq, int k, int first,
+                                    const double* uniforms, int ntrials, double* closest, double* cand_dist,
+                                    double* cums, double* pots, int32_t* cand, int32_t* idx, double* state, double* C,
+                                    int64_t ldc, void* stream) {
+  if (first < 0 || first >= n) return SCRNA_ERR_BADARG;
+  return kmeans_pp_launch(X, ldx, n, d, xsq, k, 0.0, first, uniforms, ntrials, closest, cand_dist, cums, pots, cand, idx,
+                          state, C, ldc, stream);
+}
+
 extern "C" int scrna_lloyd_assign(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc, int k,
                                   int32_t* labels, void* stream) {
   if (!X || !C || !labels || n <= 0 || d <= 0 || k <= 0 || ldx < d || ldc < d) return SCRNA_ERR_BADARG;
-  lloyd_assign_kernel<<<(unsigned)ceil_div(n, 8), 256, (size_t)k * sizeof(double), (cudaStream_t)stream>>>(
-      X, ldx, n, d, C, ldc, k, labels);
+  lloyd_assign_kernel<<<(unsigned)ceil_div(n, 8 * ASSIGN_CW), 256, (size_t)k * sizeof(double), (cudaStream_t)stream>>>(
+      X, ldx, n, d, C, ldc, k, labels, nullptr);
   return last_launch_status();
 }
 
@@ -459,9 +577,38 @@ extern "C" int scrna_lloyd_sums(const double* X, int64_t ldx, int n, int d, cons
     cudaFuncSetAttribute(lloyd_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
     attr = true;
   }
-  lloyd_sums_kernel<<<dim3((unsigned)ceil_div(d, 128), KM_SEG), 128, smem, st>>>(X, ldx, n, d, labels, k, psum, pcnt);
+  lloyd_sums_kernel<<<dim3((unsigned)ceil_div(d, 128), KM_SEG), 128, smem, st>>>(X, ldx, n, d, labels, k, psum, pcnt,
+                                                                                 nullptr);
   lloyd_sums_final_kernel<<<dim3((unsigned)ceil_div(d, 128), (unsigned)k), 128, 0, st>>>(psum, pcnt, k, d, sums, lds,
-                                                                                       counts);
+                                                                                       counts, nullptr);
+  return last_launch_status();
+}
+
+// One gated Lloyd iteration (assign -> sums -> relocate -> finish with the stop rule on the device).  The host swaps
+// Ccur / Cnxt every enqueued iteration; once state[KM_DONE] is set the remaining enqueued iterations are no-ops, and
+// the final centres are in the buffer that was `Cnxt` of iteration state[KM_ITERS].
+extern "C" int scrna_lloyd_iteration(const double* X, int64_t ldx, int n, int d, const double* Ccur, double* Cnxt,
+                                     int64_t ldc, int k, int32_t* labels, int32_t* labels_old, int32_t* counts,
+                                     double* celld, double* work, double* state, int max_iter, void* stream) {
+  if (!X || !Ccur || !Cnxt || !labels || !labels_old || !counts || !celld || !work || !state || n <= 0 || d <= 0 ||
+      k <= 0 || k > 128 || ldx < d || ldc < d || max_iter <= 0)
+    return SCRNA_ERR_BADARG;
+  double* psum = work;
+  int* pcnt = reinterpret_cast<int*>(work + (int64_t)KM_SEG * k * d);
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(lloyd_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
+    attr = true;
+  }
+  lloyd_assign_kernel<<<(unsigned)ceil_div(n, 8 * ASSIGN_CW), 256, (size_t)k * sizeof(double), st>>>(X, ldx, n, d, Ccur, ldc, k, labels,
+                                                                                         state);
+  lloyd_sums_kernel<<<dim3((unsigned)ceil_div(d, 128), KM_SEG), 128, (size_t)k * 128 * sizeof(double), st>>>(
+      X, ldx, n, d, labels, k, psum, pcnt, state);
+  lloyd_sums_final_kernel<<<dim3((unsigned)ceil_div(d, 128), (unsigned)k), 128, 0, st>>>(psum, pcnt, k, d, Cnxt, ldc,
+                                                                                       counts, state);
+  km_relocate_kernel<<<1, 1024, 0, st>>>(X, ldx, n, d, Ccur, ldc, Cnxt, ldc, counts, labels, celld, k, state);
+  lloyd_finish_kernel<<<1, 1024, 0, st>>>(Cnxt, Ccur, ldc, k, d, counts, labels, labels_old, n, state, max_iter);
   return last_launch_status();
 }
 
@@ -469,7 +616,8 @@ extern "C" int scrna_lloyd_finish(double* Cnew, const double* Cold, int64_t ldc,
                                   const int32_t* labels, int32_t* labels_old, int n, double* state, void* stream) {
   if (!Cnew || !Cold || !counts || !labels || !labels_old || !state || k <= 0 || d <= 0 || n <= 0 || ldc < d)
     return SCRNA_ERR_BADARG;
-  lloyd_finish_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(Cnew, Cold, ldc, k, d, counts, labels, labels_old, n, state);
+  lloyd_finish_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(Cnew, Cold, ldc, k, d, counts, labels, labels_old, n, state,
+                                                            0);
   return last_launch_status();
 }
 
@@ -496,6 +644,6 @@ extern "C" int scrna_km_relocate(const double* X, int64_t ldx, int n, int d, con
       ldc < d)
     return SCRNA_ERR_BADARG;
   km_relocate_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(X, ldx, n, d, Cold, ldc, sums, lds, counts, labels, celld,
-                                                          k);
+                                                          k, nullptr);
   return last_launch_status();
 }

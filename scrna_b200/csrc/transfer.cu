@@ -45,9 +45,11 @@ template <typename XT, int KP, int C, int POWER>
 __global__ void __launch_bounds__(256, 2)
 residual_kernel(const XT* __restrict__ X, int64_t ldx, int64_t panel_stride, int g, int64_t ncols,
                 const float* __restrict__ G32, const float* __restrict__ C32, int64_t ldc,
-                int rows_per_split, int tile_rows, double* __restrict__ partials) {
+                int rows_per_split, int tile_rows, double* __restrict__ partials,
+                const NmfCtrl* __restrict__ gate) {
   extern __shared__ float4 smem4[];
   __shared__ double scratch[32];
+  if (ctrl_done(gate)) return;
   const float* sW = reinterpret_cast<const float*>(smem4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t j0 = ((int64_t)blockIdx.x * 8 + warp) * (32 * C) + (int64_t)lane * C;
@@ -127,8 +129,9 @@ residual_kernel(const XT* __restrict__ X, int64_t ldx, int64_t panel_stride, int
 }
 
 __global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double* __restrict__ out,
-                                    double scale) {
+                                    double scale, const NmfCtrl* __restrict__ gate = nullptr) {
   __shared__ double scratch[32];
+  if (ctrl_done(gate)) return;
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
   s = block_sum(s, scratch);
@@ -241,7 +244,7 @@ struct ResCfg {
 template <typename XT, int KP>
 static int residual_launch(const XT* X, int64_t ldx, int64_t panel_stride, int g, int64_t ncols, const float* G32,
                            const float* C32, int64_t ldc, int power, double* partials, double* out,
-                           int nsplit, cudaStream_t st) {
+                           int nsplit, cudaStream_t st, const NmfCtrl* gate = nullptr) {
   constexpr int C = ResCfg<KP>::C;
   const int rps = (int)ceil_div(g, nsplit);
   int tr = (32 * 1024) / (KP * 4);
@@ -252,11 +255,11 @@ static int residual_launch(const XT* X, int64_t ldx, int64_t panel_stride, int g
   const size_t smem = (size_t)tr * KP * sizeof(float);
   if (power == 1)
     residual_kernel<XT, KP, C, 1><<<grid, 256, smem, st>>>(X, ldx, panel_stride, g, ncols, G32, C32, ldc, rps, tr,
-                                                           partials);
+                                                           partials, gate);
   else
     residual_kernel<XT, KP, C, 2><<<grid, 256, smem, st>>>(X, ldx, panel_stride, g, ncols, G32, C32, ldc, rps, tr,
-                                                           partials);
-  sum_partials_kernel<<<1, 256, 0, st>>>(partials, (int)(grid.x * grid.y), out, 1.0);
+                                                           partials, gate);
+  sum_partials_kernel<<<1, 256, 0, st>>>(partials, (int)(grid.x * grid.y), out, 1.0, gate);
   return last_launch_status();
 }
 
@@ -339,6 +342,58 @@ extern "C" int scrna_transfer_mu_step(double* H64, float* H32, const double* WtX
   const size_t smem = (size_t)kp * kp * sizeof(double);
   transfer_mu_step_kernel<<<(unsigned)ceil_div(ncols, 128), 128, smem, (cudaStream_t)stream>>>(
       H64, H32, WtX, WtW, k, kp, ncols, ldc, (NmfCtrl*)ctrl);
+  return last_launch_status();
+}
+
+// The stop rule of utils.get_transferred_data_matrix (utils.py:202-205) on the device: one thread turns the reduced
+// residual into the mean absolute error, compares it with the previous one and sets ctrl->done; every kernel of a later
+// enqueued iteration (K6, the gated residual, this one) then returns at once, so the host polls once per batch.
+__global__ void transfer_stop_kernel(const double* __restrict__ res, double denom, double rel_err, int max_iter,
+                                     NmfCtrl* __restrict__ ctrl) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || ctrl->done) return;
+  const double new_err = res[0] / denom;
+  const int it = ++ctrl->iter;
+  const double err = it == 1 ? 1e10 : ctrl->reserved[0];
+  ctrl->err_last = new_err;
+  bool stop = (ctrl->flags & SCRNA_FLAG_ZERO_DEN) != 0;
+  if (!stop && fabs((err - new_err) / err) <= rel_err && err >= new_err) stop = true;
+  if (!stop) {
+    ctrl->reserved[0] = new_err;
+    stop = it >= max_iter;
+  }
+  if (stop) {
+    ctrl->n_iter = it;
+    ctrl->done = 1;
+  }
+}
+
+extern "C" int scrna_transfer_iteration(const void* X, int x_is_f16, int64_t ldx, int g, int64_t n, int64_t ncols,
+                                        const float* G32, double* H64, float* H32, const double* WtX,
+                                        const double* WtW, int k, int kp, int64_t ldc, double* partials, double* out,
+                                        scrna_nmf_ctrl_t* ctrl, void* stream) {
+  if (!X || !G32 || !H64 || !H32 || !WtX || !WtW || !partials || !out || !ctrl || k <= 0 || k > kp ||
+      kp > SCRNA_MAX_K || g <= 0 || n <= 0 || n > ncols || ncols > ldc || (ldc & 3) || (ncols & 3) ||
+      (x_is_f16 ? ldx < g : ((ldx & 3) || ncols > ldx)))
+    return SCRNA_ERR_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const NmfCtrl* gate = (const NmfCtrl*)ctrl;
+  transfer_mu_step_kernel<<<(unsigned)ceil_div(n, 128), 128, (size_t)kp * kp * sizeof(double), st>>>(
+      H64, H32, WtX, WtW, k, kp, n, ldc, (NmfCtrl*)ctrl);
+  SCRNA_DISPATCH_KP_T(kp, {
+    const int64_t tiles = ceil_div(ncols, 8 * 32 * ResCfg<KP>::C);
+    if (x_is_f16)
+      return residual_launch<__half, KP>(reinterpret_cast<const __half*>(X), 256, ldx * 256, g, ncols, G32, H32, ldc, 1,
+                                         partials, out, residual_splits(g, tiles), st, gate);
+    return residual_launch<float, KP>(reinterpret_cast<const float*>(X), ldx, 0, g, ncols, G32, H32, ldc, 1, partials,
+                                      out, residual_splits(g, tiles), st, gate);
+  });
+  return SCRNA_ERR_UNSUPPORTED;
+}
+
+extern "C" int scrna_transfer_stop(const double* res, double denom, double rel_err, int max_iter,
+                                   scrna_nmf_ctrl_t* ctrl, void* stream) {
+  if (!res || !ctrl || !(denom > 0.0) || max_iter <= 0) return SCRNA_ERR_BADARG;
+  transfer_stop_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(res, denom, rel_err, max_iter, (NmfCtrl*)ctrl);
   return last_launch_status();
 }
 

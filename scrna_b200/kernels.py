@@ -195,6 +195,15 @@ class CudaKernels:
     def transfer_mu_step(self, H64, H32, WtX, WtW, k, kp, ncols, ldc, ctrl):
         self._call("scrna_transfer_mu_step", H64, H32, WtX, WtW, k, kp, ncols, ldc, ctrl, self._s())
 
+    def transfer_iteration(self, X, ldx, g, n, ncols, G32, H64, H32, WtX, WtW, k, kp, ldc, partials, out, ctrl):
+        self.launches += 3
+        self._call("scrna_transfer_iteration", X, int(X.dtype == self.torch.float16), ldx, g, n, ncols, G32, H64, H32, WtX,
+                   WtW, k, kp, ldc, partials, out, ctrl, self._s())
+
+    def transfer_stop(self, out, denom, rel_err, max_iter, ctrl):
+        self.launches += 1
+        self._call("scrna_transfer_stop", out, float(denom), float(rel_err), int(max_iter), ctrl, self._s())
+
     def argmax_cols(self, H64, k, ncols, ldc, labels):
         self._call("scrna_argmax_cols", H64, k, ncols, ldc, labels, self._s())
 

@@ -39,6 +39,7 @@ class Sc3Ops:
         self.kn = kernels
         self.torch = kernels.torch
         self.dev = self.torch.device("cuda", self.torch.cuda.current_device())
+        self._uniform_cdf = {}
         self.stage_seconds = None   # bench.py sets a dict: synchronised wall seconds accumulated per stage
         self.svd_flops = 0.0
         self.jacobi_sweeps = 0
@@ -339,37 +340,53 @@ class Sc3Ops:
         counts = self.zeros(k, dtype=i32)
         celld = self.empty(n)
         sums_work = self.empty(_lib.call("scrna_lloyd_sums_work_elems", k, d))
-        best = None
         esz = 8
         self.km_iters = 0
+        bufs = (Ca, Cb)
+        # first centre of every restart: RandomState.choice(n, p=full(n, 1/n)) (SP/sklearn/cluster/_kmeans.py:231) is
+        # searchsorted(cdf, u, side='right') on the sequentially accumulated cdf -- NumPy's own arithmetic, once per n
+        cdf = self._uniform_cdf.get(n)
+        if cdf is None:
+            cdf = np.full(n, 1.0 / n).cumsum()
+            cdf /= cdf[-1]
+            self._uniform_cdf = {n: cdf}
+        firsts = np.minimum(np.searchsorted(cdf, draws[: n_init * per: per], side="right"), n - 1)
+        runs_labels = self.zeros(n_init, n, dtype=i32)
+        inertias = self.zeros(n_init)
+        batch = 8   # Lloyd iterations enqueued between two polls of the device-side stop flag
         for r in range(n_init):
-            u0 = float(draws[r * per])
+            first = int(firsts[r])
             uptr = U.data_ptr() + (r * per + 1) * esz
-            self._call("scrna_kmeans_pp", X, d, n, d, xsq, k, u0, uptr if k > 1 else None, trials, closest,
+            self._call("scrna_kmeans_pp_from", X, d, n, d, xsq, k, first, uptr if k > 1 else None, trials, closest,
                        cand_dist, cums, pots, cand, idx, state, Ca, d, self._s(), launches=4 * k + 1)
             labels_old.fill_(-1)
-            cur, nxt = Ca, Cb
-            strict = False
-            for _ in range(max_iter):
-                self._call("scrna_lloyd_assign", X, d, n, d, cur, d, k, labels, self._s())
-                self._call("scrna_lloyd_sums", X, d, n, d, labels, k, nxt, d, counts, sums_work, self._s(), launches=2)
-                self._call("scrna_km_relocate", X, d, n, d, cur, d, nxt, d, counts, labels, celld, k, self._s())
-                self._call("scrna_lloyd_finish", nxt, cur, d, k, d, counts, labels, labels_old, n, state, self._s())
-                st = state.cpu().numpy()
-                self.km_iters += 1
-                cur, nxt = nxt, cur
-                if st[4] == 0.0:
-                    strict = True
+            state[6:8].zero_()
+            queued, st = 0, None
+            while queued < max_iter:
+                nb = min(batch, max_iter - queued)
+                for b in range(nb):
+                    cur, nxt = bufs[(queued + b) % 2], bufs[(queued + b + 1) % 2]
+                    self._call("scrna_lloyd_iteration", X, d, n, d, cur, nxt, d, k, labels, labels_old, counts, celld,
+                               sums_work, state, int(max_iter), self._s(), launches=5)
+                queued += nb
+                st = state.cpu().numpy()          # one poll per batch (the stop rule itself lives on the device)
+                if st[6] != 0.0:
                     break
-                if st[2] <= tol:
-                    break
-            if not strict:
+            done_iters = int(st[7])
+            self.km_iters += done_iters
+            cur = bufs[done_iters % 2]             # the centres the last executed iteration wrote
+            if st[6] != 1.0:                       # not strict convergence: labels of the final centres
                 self._call("scrna_lloyd_assign", X, d, n, d, cur, d, k, labels, self._s())
             self._call("scrna_km_inertia", X, d, n, d, cur, d, labels, celld, state, self._s(), launches=2)
-            inertia = float(state.cpu()[3])
-            lab_host = labels.cpu().numpy()
-            if best is None or (inertia < best[1] and not same_clustering(lab_host, best[0], k)):
-                best = (lab_host.copy(), inertia)
+            inertias[r: r + 1].copy_(state[3:4])
+            runs_labels[r].copy_(labels)
+        # restart selection on the host from ONE read-back (sklearn _kmeans.py:1534-1541)
+        inert = inertias.cpu().numpy()
+        labs = runs_labels.cpu().numpy()
+        best = None
+        for r in range(n_init):
+            if best is None or (inert[r] < best[1] and not same_clustering(labs[r], best[0], k)):
+                best = (labs[r].copy(), float(inert[r]))
         return best[0]
 
     # ---- a15 / a17 consensus --------------------------------------------------------------------------

@@ -78,27 +78,35 @@ class TransferSession:
             self.comm.all_reduce(self.res_out)
         return float(self.res_out.cpu()[0]) / float(X.g * self.n_total)
 
+    POLL_EVERY = 4   # iterations enqueued between two reads of the control block
+
     def solve(self, H0, max_iter=100, rel_err=1e-3):
-        """The reference loop (utils.py:195-206) from an injected H0.  Returns (n_iter, err)."""
+        """The reference loop (utils.py:195-206) from an injected H0.  Returns (n_iter, err).  The stop rule runs on
+        the device (scrna_transfer_stop); the host enqueues POLL_EVERY iterations at a time and reads the control
+        block once per batch -- iterations enqueued past the stop are no-ops."""
         self._set_H(H0)
         self.kn.ctrl_reset(self.ctrl)
         X = self.X
-        n_iter = 0
-        err = 1e10
-        new_err = None
-        while n_iter < max_iter:
-            n_iter += 1
-            self.kn.transfer_mu_step(self.H64, self.H32, self.WtX, self.WtW, self.k, self.kp, X.n, self.ldc,
-                                     self.ctrl)
-            new_err = self.l1_error()   # synchronises: the stop rule is a host decision on one scalar
-            if self._flags() & _lib.FLAG_ZERO_DEN:
+        denom = float(X.g * self.n_total)
+        queued = 0
+        raw = None
+        while queued < max_iter:
+            nb = min(self.POLL_EVERY, max_iter - queued)
+            for _ in range(nb):
+                self.kn.transfer_iteration(X.data, X.ldx, X.g, X.n, X.ncols, self.G32, self.H64, self.H32, self.WtX, self.WtW,
+                                           self.k, self.kp, self.ldc, self.res_part, self.res_out, self.ctrl)
+                if self.comm is not None:
+                    self.comm.all_reduce(self.res_out)
+                self.kn.transfer_stop(self.res_out, denom, rel_err, max_iter, self.ctrl)
+            queued += nb
+            raw = self.ctrl.cpu().numpy()
+            if raw[3] & _lib.FLAG_ZERO_DEN:
                 raise Exception('DA target: division by zero.')
-            if np.abs((err - new_err) / err) <= rel_err and err >= new_err:
+            if raw[1]:
                 break
-            err = new_err
-        self.n_iter = n_iter
-        self.err = new_err
-        return n_iter, new_err
+        self.n_iter = int(raw[2]) if raw is not None else 0
+        self.err = float(raw.view(np.float64)[4]) if raw is not None else None
+        return self.n_iter, self.err
 
     def labels(self):
         X = self.X

@@ -23,9 +23,14 @@ for rep in range(2):
     sc3.add_intermediate_clustering(partial(sc.intermediate_kmeans_clustering, k=k))
     sc3.set_build_consensus_matrix(sc.build_consensus_matrix)
     sc3.set_consensus_clustering(partial(sc.consensus_clustering, n_components=k))
+    ops = sc._ops()
+    ops.stage_seconds = {} if os.environ.get("STAGES", "1") == "1" else None
     torch.cuda.synchronize(); t0 = time.perf_counter()
     sc3.apply()
     torch.cuda.synchronize(); out["apply_s_run%d" % rep] = time.perf_counter() - t0
+    if ops.stage_seconds is not None:
+        out["stages_run%d" % rep] = {a: round(b, 4) for a, b in ops.stage_seconds.items()}
+    ops.stage_seconds = None
 from sklearn.metrics import adjusted_rand_score
 out["ari_vs_simulated"] = float(adjusted_rand_score(lab, sc3.cluster_labels))
 print(json.dumps(out))
