@@ -580,6 +580,7 @@ def run_gpu(args):
         shutdown_distributed(world)
         return
     slv_tc, slv_half, slv_kp, payload = bool(slv.tc), bool(slv.half), slv.kp, int(slv.R.numel())
+    slv_parts = int(getattr(slv, "h_parts", 0) or 0)
     if getattr(slv, "fused", False):
         nb = kn.h_nb(slv.kp, slv.h_parts)
         exchange = ("fused gene step (nmf_step.cu): %d B of NVLink peer loads + %d B of peer stores per rank per iteration "
@@ -654,7 +655,11 @@ def run_gpu(args):
                        "genes": genes, "cells": cells, "k": k, "solver": "mu", "l1": L1, "l2": L2,
                        "x_storage": ("fp16 (every count exactly representable) genes x cells + resident transposed copy"
                                      if slv_half else "fp32 genes x cells + resident transposed copy"),
-                       "sweep": ("tcgen05 kind::f16, 3-part fp16 factor split (kq=%d)" % slv_kp if slv_half else
+                       "arithmetic": ("X stored and multiplied as fp16 (exact for counts), factor as a %d-part scaled fp16 "
+                                      "split, fp32 accumulation in tensor memory drained every 128 rows, fp64 masters / "
+                                      "updates / stop rules" % slv_parts if slv_half else
+                                      "fp32 storage, fp32 accumulation, fp64 masters / updates / stop rules"),
+                       "sweep": ("tcgen05 kind::f16, %d-part fp16 factor split (kq=%d)" % (slv_parts, slv_kp) if slv_half else
                                  "tcgen05 3xTF32 (kp=%d)" % slv_kp if slv_tc else "fp32 FMA (kp=%d)" % slv_kp),
                        "l2_flush": "none needed: each sweep streams %.1f GB per GPU, far larger than the 126 MB L2"
                                    % (genes * n_loc * xbytes / 1e9),

@@ -354,7 +354,10 @@ int scrna_gather_rows_scaled_f64(const double* W, int64_t ld, int n, const int32
                                  double* out, int64_t ldo, void* stream);
 
 /* K14-K17 k-means as sklearn KMeans(init='k-means++', algorithm='lloyd') runs it
- * (sc3_clustering_impl.py:215-217).  state: 8 doubles {tol, potential, shift_tot, inertia, changed, n_empty}. */
+ * (sc3_clustering_impl.py:215-217).  state: 8 doubles {tol, potential, shift_tot, inertia, changed, n_empty, done,
+ * iterations}.  scrna_km_prepare: X = V[:, :d] - column means, xsq = squared row norms, state[0] = tol
+ * (1e-4 x mean column variance); work: scrna_km_prepare_work_elems(d) doubles. */
+int64_t scrna_km_prepare_work_elems(int d);
 int scrna_km_prepare(const double* V, int64_t ldv, int n, int d, double* X, int64_t ldx, double* xsq,
                      double* work, double* state, void* stream);
 int scrna_kmeans_pp(const double* X, int64_t ldx, int n, int d, const double* xsq, int k, double u0,
@@ -368,6 +371,14 @@ int scrna_kmeans_pp_from(const double* X, int64_t ldx, int n, int d, const doubl
                          const double* uniforms, int ntrials, double* closest, double* cand_dist, double* cums,
                          double* pots, int32_t* cand, int32_t* idx, double* state, double* C, int64_t ldc,
                          void* stream);
+/* k-means++ of all n_init restarts of a fit in one launch sequence (the restart is a grid dimension of every kernel):
+ * firsts: n_init first centres (device int32), uniforms: n_init * (1 + (k-1)*ntrials) doubles in the reference's draw
+ * order (the first of each restart is the one the host turned into `firsts`), closest / cums: n_init x n, cand_dist:
+ * n_init x ntrials x n, pots / cand: n_init x 8, idx: n_init x k, state: n_init x 8, C: n_init x k x ldc. */
+int scrna_kmeans_pp_batched(const double* X, int64_t ldx, int n, int d, const double* xsq, int k, int n_init,
+                            const int32_t* firsts, const double* uniforms, int ntrials, double* closest,
+                            double* cand_dist, double* cums, double* pots, int32_t* cand, int32_t* idx, double* state,
+                            double* C, int64_t ldc, void* stream);
 int scrna_lloyd_assign(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc, int k,
                        int32_t* labels, void* stream);
 int64_t scrna_lloyd_sums_work_elems(int k, int d);
@@ -382,6 +393,19 @@ int scrna_lloyd_finish(double* Cnew, const double* Cold, int64_t ldc, int k, int
 int scrna_lloyd_iteration(const double* X, int64_t ldx, int n, int d, const double* Ccur, double* Cnxt, int64_t ldc,
                           int k, int32_t* labels, int32_t* labels_old, int32_t* counts, double* celld, double* work,
                           double* state, int max_iter, void* stream);
+/* All n_init restarts of a fit in one launch set per Lloyd iteration: the assignment is one fp64 GEMM
+ * X (n x d) . C^T (d x n_init*k) on the FP64 tensor cores (DMMA) with the argmin as its epilogue, the centre sums
+ * read X once for all restarts; a restart whose stop rule has fired is skipped tile by tile.  Ccur / Cnxt:
+ * n_init x k x ldc (swapped by the host every call), labels / labels_old: n_init x n, counts: n_init x k, celld:
+ * n_init x n, state: n_init x 8 (per restart: [0] = tol, [6..7] zeroed before the first call), work:
+ * scrna_lloyd_batched_work_elems doubles.  ldx, ldc even; X, C 16-byte aligned.
+ * scrna_lloyd_batched_supported: n_init <= 16, k <= 48, n_init * k <= 400. */
+int scrna_lloyd_batched_supported(int k, int n_init);
+int64_t scrna_lloyd_batched_work_elems(int k, int d, int n_init);
+int scrna_lloyd_iteration_batched(const double* X, int64_t ldx, int n, int d, const double* Ccur, double* Cnxt,
+                                  int64_t ldc, int k, int n_init, int32_t* labels, int32_t* labels_old,
+                                  int32_t* counts, double* celld, double* work, double* state, int max_iter,
+                                  void* stream);
 int scrna_km_cell_dist(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc,
                        const int32_t* labels, double* out, void* stream);
 int scrna_km_inertia(const double* X, int64_t ldx, int n, int d, const double* C, int64_t ldc,

@@ -112,6 +112,8 @@ _SIGNATURES = {
     "scrna_km_prepare": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_kmeans_pp": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_dbl, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                         c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
+    "scrna_kmeans_pp_batched": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr,
+                                c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     "scrna_kmeans_pp_from": [c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                              c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     "scrna_lloyd_assign": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_int, c_ptr, c_ptr],
@@ -123,6 +125,11 @@ _SIGNATURES = {
     "scrna_transfer_stop": [c_ptr, c_dbl, c_dbl, c_int, c_ptr, c_ptr],
     "scrna_lloyd_iteration": [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                               c_ptr, c_int, c_ptr],
+    "scrna_lloyd_batched_supported": [c_int, c_int],
+    "scrna_lloyd_batched_work_elems": [c_int, c_int, c_int],
+    "scrna_lloyd_iteration_batched": [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr,
+                                      c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr],
+    "scrna_km_prepare_work_elems": [c_int],
     "scrna_km_cell_dist": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr],
     "scrna_km_inertia": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "scrna_km_relocate": [c_ptr, c_i64, c_int, c_int, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_int, c_ptr],
@@ -137,11 +144,13 @@ _VALUE_RETURNING = {"scrna_abi_version", "scrna_nmf_xht_splits", "scrna_nmf_wtx_
                     "scrna_nmf_tc_shadow_elems", "scrna_bjacobi_blocks", "scrna_bjacobi_splits",
                     "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems", "scrna_kta_blocks",
                     "scrna_nmf_h_supported", "scrna_nmf_h_nb", "scrna_nmf_h_shadow_elems", "scrna_nmf_wtx_h_splits",
-                    "scrna_f16_panel_rows", "scrna_f16_panel_elems", "scrna_nmf_h_groups", "scrna_nmf_step_groups", "scrna_sytrd_work_elems"}
+                    "scrna_f16_panel_rows", "scrna_f16_panel_elems", "scrna_nmf_h_groups", "scrna_nmf_step_groups", "scrna_sytrd_work_elems",
+                    "scrna_lloyd_batched_supported", "scrna_lloyd_batched_work_elems", "scrna_km_prepare_work_elems"}
 
 
 _RETURNS_I64 = {"scrna_sytrd_work_elems", "scrna_nmf_tc_shadow_elems", "scrna_nmf_h_shadow_elems", "scrna_f16_panel_rows", "scrna_f16_panel_elems",
-                "scrna_nmf_h_groups", "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems"}
+                "scrna_nmf_h_groups", "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems",
+                "scrna_lloyd_batched_work_elems", "scrna_km_prepare_work_elems"}
 
 
 class ScrnaError(RuntimeError):

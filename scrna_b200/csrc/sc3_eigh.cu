@@ -111,6 +111,77 @@ eh_symv_kernel(const double* __restrict__ A, int64_t ld, int n, int c, const dou
   if (lane == 0) y[r] = t;
 }
 
+// ---- k3 (shipped): the same product reading ONE triangle.  A22 is symmetric, so every 128 x 128 tile (I, J) of the
+// upper triangle (absolute 128-aligned blocks, J >= I) serves two pieces of y: rows of block I (A_IJ v_J) and, for
+// J > I, rows of block J (A_IJ^T v_I) -- half the HBM traffic of the row-per-warp kernel above.  The pieces go to slabs
+// (PR[J][r in block I], PC[I][s in block J]) that k5 adds up in a fixed order: deterministic, no atomics.
+constexpr int EH_SB = 128;
+__global__ void __launch_bounds__(256)
+eh_symv_upper_kernel(const double* __restrict__ A, int64_t ld, int n, int c, const double* __restrict__ x,
+                     const double* __restrict__ scal, double* __restrict__ PR, double* __restrict__ PC) {
+  __shared__ double vI[EH_SB], vJ[EH_SB], cpart[8][EH_SB];
+  const int lo = c + 1;
+  const int b0 = lo / EH_SB, T = (n - 1) / EH_SB - b0 + 1;
+  // linear tile index -> (I, J) of the upper triangle, row by row: row a holds T - a tiles
+  const int t = blockIdx.x;
+  int a = (int)(((2.0 * T + 1.0) - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)t)) * 0.5);
+  while (a > 0 && (int64_t)a * T - (int64_t)a * (a - 1) / 2 > t) --a;
+  while ((int64_t)(a + 1) * T - (int64_t)(a + 1) * a / 2 <= t) ++a;
+  const int I = b0 + a, J = I + (t - (int)((int64_t)a * T - (int64_t)a * (a - 1) / 2));
+  const int I0 = I * EH_SB, J0 = J * EH_SB;
+  const double sc = scal[0];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < EH_SB) {
+    const int s = I0 + tid;
+    vI[tid] = (s < lo || s >= n) ? 0.0 : (s == lo ? 1.0 : x[s] * sc);
+  } else {
+    const int s = J0 + tid - EH_SB;
+    vJ[tid - EH_SB] = (s < lo || s >= n) ? 0.0 : (s == lo ? 1.0 : x[s] * sc);
+  }
+  __syncthreads();
+  const bool offdiag = J > I;
+  double cacc[4] = {0.0, 0.0, 0.0, 0.0};
+  double vj[4];
+  bool cok[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    vj[q] = vJ[lane + 32 * q];
+    const int s = J0 + lane + 32 * q;
+    cok[q] = s >= lo && s < n;
+  }
+  double* pr = PR + (int64_t)(J - b0) * n;
+#pragma unroll 4
+  for (int rr = 0; rr < 16; ++rr) {
+    const int rl = warp * 16 + rr, r = I0 + rl;
+    if (r < lo || r >= n) continue;                       // uniform over the warp
+    const double* row = A + (int64_t)r * ld + J0 + lane;
+    double av[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) av[q] = cok[q] ? row[32 * q] : 0.0;
+    const double vi = vI[rl];
+    double rs = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      rs = fma(av[q], vj[q], rs);
+      cacc[q] = fma(av[q], vi, cacc[q]);
+    }
+    rs = warp_sum(rs);
+    if (lane == 0) pr[r] = rs;
+  }
+  if (offdiag) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cpart[warp][lane + 32 * q] = cacc[q];
+    __syncthreads();
+    if (tid < EH_SB) {
+      double s8 = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s8 += cpart[w][tid];    // fixed order
+      const int sabs = J0 + tid;
+      if (sabs < n) PC[(int64_t)(I - b0) * n + sabs] = s8;
+    }
+  }
+}
+
 // ---- k4: t1 = Wp . v, t2 = Vp . v (rows of the panel buffers against v); v is stored scaled -------------------------
 __global__ void __launch_bounds__(256)
 eh_panel_dots_kernel(int n, int c, int i, double* __restrict__ Vp, const double* __restrict__ Wp,
@@ -154,7 +225,8 @@ eh_panel_dots_kernel(int n, int c, int i, double* __restrict__ Vp, const double*
 // ---- k5: w' = y - Vp^T t1 - Wp^T t2 ; partial w'.v ------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 eh_w_kernel(int n, int c, int i, const double* __restrict__ Vp, const double* __restrict__ Wp,
-            const double* __restrict__ dots_part, int nparts, const double* __restrict__ y, double* __restrict__ w,
+            const double* __restrict__ dots_part, int nparts, const double* __restrict__ y,
+            const double* __restrict__ PR, const double* __restrict__ PC, double* __restrict__ w,
             double* __restrict__ part) {
   __shared__ double t1[EH_NB], t2[EH_NB], scratch[32];
   if (threadIdx.x < 2 * i) {
@@ -166,8 +238,17 @@ eh_w_kernel(int n, int c, int i, const double* __restrict__ Vp, const double* __
   __syncthreads();
   const double* vi = Vp + (int64_t)i * n;
   double dot = 0.0;
+  const int b0 = (c + 1) / EH_SB, B = (n - 1) / EH_SB;
   for (int r = c + 1 + blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-    double v = y[r];
+    double v;
+    if (PR) {   // y[r] from the slabs of eh_symv_upper_kernel: tiles (I(r), J >= I(r)), then tiles (I < I(r), I(r))
+      const int Ir = r / EH_SB;
+      v = 0.0;
+      for (int J = Ir; J <= B; ++J) v += PR[(int64_t)(J - b0) * n + r];
+      for (int I = b0; I < Ir; ++I) v += PC[(int64_t)(I - b0) * n + r];
+    } else {
+      v = y[r];
+    }
     for (int p = 0; p < i; ++p) v -= Vp[(int64_t)p * n + r] * t1[p] + Wp[(int64_t)p * n + r] * t2[p];
     w[r] = v;
     dot = fma(v, vi[r], dot);
@@ -203,7 +284,7 @@ constexpr int EH_TP = 64 + 8;      // pitch of the staged 64 x 64 row operand   
 constexpr int EH_TQ = 128 + 8;     // pitch of the staged 64 x 128 column operand [k][s]
 __global__ void __launch_bounds__(256)
 eh_syr2k_kernel(double* __restrict__ A, int64_t ld, int n, int lo, int nb, const double* __restrict__ Vp,
-                const double* __restrict__ Wp) {
+                const double* __restrict__ Wp, int upper_only) {
   extern __shared__ __align__(16) double eh_smem[];
   double* P = eh_smem;                 // [k < 64][r < 64]
   double* Q = P + 64 * EH_TP;          // [k < 64][s < 128]
@@ -211,6 +292,9 @@ eh_syr2k_kernel(double* __restrict__ A, int64_t ld, int n, int lo, int nb, const
   const int wr = warp >> 2, wc = warp & 3;
   const int lr = lane >> 2, lk = lane & 3;
   const int r0 = lo + blockIdx.y * 64, s0 = lo + blockIdx.x * 128;
+  // only the upper triangle by 128-aligned blocks (columns in a block >= the row's block) is read again (k1 reads
+  // row c to the right of the diagonal, eh_symv_upper_kernel tiles J >= I): tiles entirely left of it are skipped
+  if (upper_only && s0 + 127 < (r0 / EH_SB) * EH_SB) return;
   for (int e = tid; e < 64 * 64; e += 256) {
     const int k = e >> 6, r = e & 63;
     const double* src = (k < 32 ? Vp + (int64_t)k * n : Wp + (int64_t)(k - 32) * n);
@@ -492,9 +576,11 @@ eh_backtransform_smem_kernel(const double* __restrict__ A, int64_t ld, int n, co
 
 using namespace scrna;
 
-// work: 2 * 32 * n (Vp, Wp) + 3 * n (x, y, w) + 256 * 66 (partials) + 8 doubles
+// work: 2 * 32 * n (Vp, Wp) + 3 * n (x, y, w) + 256 * 66 (partials) + 8 doubles + 2 * ceil(n / 128) * n (symv slabs)
 extern "C" int64_t scrna_sytrd_work_elems(int n) {
-  return n > 0 ? (int64_t)2 * EH_NB * n + 3 * (int64_t)n + (int64_t)EH_RED * (2 * EH_NB + 2) + 8 : SCRNA_ERR_BADARG;
+  return n > 0 ? (int64_t)2 * EH_NB * n + 3 * (int64_t)n + (int64_t)EH_RED * (2 * EH_NB + 2) + 8 +
+                     2 * ceil_div(n, EH_SB) * (int64_t)n   // slabs of the one-triangle symv
+               : SCRNA_ERR_BADARG;
 }
 
 extern "C" int scrna_sytrd_f64(double* A, int64_t ld, int n, double* d, double* e, double* tau, double* work,
@@ -510,6 +596,8 @@ extern "C" int scrna_sytrd_f64(double* A, int64_t ld, int n, double* d, double* 
   double* dpart = part + EH_RED;                          // EH_RED * 64
   double* part2 = dpart + (int64_t)EH_RED * 2 * EH_NB;    // EH_RED
   double* scal = part2 + EH_RED;                          // 8
+  double* PR = scal + 8;                                  // ceil(n/128) x n
+  double* PC = PR + ceil_div(n, EH_SB) * (int64_t)n;      // ceil(n/128) x n
   static bool attr = false;
   const size_t smem_up = (size_t)(64 * EH_TP + 64 * EH_TQ) * sizeof(double);
   if (!attr) {
@@ -526,17 +614,20 @@ extern "C" int scrna_sytrd_f64(double* A, int64_t ld, int n, double* d, double* 
       if (blocks > EH_RED) blocks = EH_RED;
       eh_col_kernel<<<blocks, 256, 0, st>>>(A, ld, n, c, i, Vp, Wp, x, part, d, scal);
       eh_house_kernel<<<1, 32, 0, st>>>(part, blocks, c, e, tau, scal);
-      eh_symv_kernel<<<(m - 1 + 7) / 8, 256, 0, st>>>(A, ld, n, c, x, scal, y);
+      {
+        const int64_t T = (n - 1) / EH_SB - (c + 1) / EH_SB + 1;
+        eh_symv_upper_kernel<<<(unsigned)(T * (T + 1) / 2), 256, 0, st>>>(A, ld, n, c, x, scal, PR, PC);
+      }
       int vb = (n + 255) / 256;
       if (vb > EH_RED) vb = EH_RED;
       eh_panel_dots_kernel<<<vb, 256, 0, st>>>(n, c, i, Vp, Wp, x, scal, A + (int64_t)c * ld, dpart);
-      eh_w_kernel<<<blocks, 256, 0, st>>>(n, c, i, Vp, Wp, dpart, vb, y, w, part2);
+      eh_w_kernel<<<blocks, 256, 0, st>>>(n, c, i, Vp, Wp, dpart, vb, y, PR, PC, w, part2);
       eh_wfin_kernel<<<vb, 256, 0, st>>>(n, c, i, Vp, Wp, w, part2, blocks, scal);
     }
     const int lo = j + nb;
     if (lo < n) {
       dim3 grid((unsigned)ceil_div(n - lo, 128), (unsigned)ceil_div(n - lo, 64));
-      eh_syr2k_kernel<<<grid, 256, smem_up, st>>>(A, ld, n, lo, nb, Vp, Wp);
+      eh_syr2k_kernel<<<grid, 256, smem_up, st>>>(A, ld, n, lo, nb, Vp, Wp, 1);
     }
   }
   // the last 2 x 2 block: d[n-2], d[n-1], e[n-2] are what is left in A; no reflector

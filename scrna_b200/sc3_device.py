@@ -302,13 +302,17 @@ class Sc3Ops:
         return out
 
     # ---- a14 k-means ----------------------------------------------------------------------------------
-    def kmeans(self, V, d, k, draws, n_init=10, max_iter=10000):
+    def kmeans(self, V, d, k, draws, n_init=10, max_iter=10000, batched=None):
         """KMeans(n_clusters=k, n_init, max_iter, init='k-means++').fit_predict(V[:, :d]); `draws` are the
-        n_init * kmeans_draw_count(k) uniforms of the reference's RNG stream.  Returns int32 device labels."""
+        n_init * kmeans_draw_count(k) uniforms of the reference's RNG stream.  Returns int64 host labels.
+        batched: run the Lloyd iterations of all restarts in one launch set (None: whenever the kernels take the
+        shape -- n_init <= 16, k <= 48); False keeps one restart after the other (any k <= 128)."""
         with self._stage("kmeans_ensemble"):
-            return self._kmeans(V, d, k, draws, n_init, max_iter)
+            return self._kmeans(V, d, k, draws, n_init, max_iter, batched)
 
-    def _kmeans(self, V, d, k, draws, n_init, max_iter):
+    KM_POLL = 8   # Lloyd iterations enqueued between two polls of the device-side stop flags
+
+    def _kmeans(self, V, d, k, draws, n_init, max_iter, batched=None):
         t = self.torch
         V = self.to_device(V)
         n, ldv = V.shape[0], V.stride(0)
@@ -319,30 +323,35 @@ class Sc3Ops:
         draws = np.ascontiguousarray(draws, dtype=np.float64)
         if draws.size < n_init * per:
             raise ValueError("need %d uniforms, got %d" % (n_init * per, draws.size))
+        can_batch = bool(_lib.call("scrna_lloyd_batched_supported", int(k), int(n_init)))
+        if batched is None:
+            batched = can_batch
+        elif batched and not can_batch:
+            raise ValueError("the batched k-means kernels take n_init <= 16, k <= 48 and n_init * k <= 200")
         i32 = t.int32
-        X = self.empty(n, d)
+        ld = ((d + 3) // 4) * 4                 # 32-byte rows: the batched assignment stages them with 16-byte copies
+        X = self.empty(n, ld)
         xsq = self.empty(n)
-        work = self.empty(2 * d)
-        state = self.zeros(8)
-        self._call("scrna_km_prepare", V, ldv, n, d, X, d, xsq, work, state, self._s(), launches=3)
-        tol = float(state.cpu()[0])
+        work = self.empty(_lib.call("scrna_km_prepare_work_elems", int(d)))
+        R = int(n_init)
+        state = self.zeros(R, 8)                # one control block per restart ([0] tol, [3] inertia, [6] done, [7] iterations)
+        self._call("scrna_km_prepare", V, ldv, n, d, X, ld, xsq, work, state, self._s(), launches=3)
+        state[1:, 0] = state[0, 0]
         U = t.from_numpy(draws).to(self.dev)
-        closest = self.empty(n)
-        cand_dist = self.empty(trials * n)
-        cums = self.empty(n)
-        pots = self.empty(8)
-        cand = self.zeros(8, dtype=i32)
-        idx = self.zeros(k, dtype=i32)
-        Ca = self.empty(k, d)
-        Cb = self.empty(k, d)
-        labels = self.zeros(n, dtype=i32)
-        labels_old = self.zeros(n, dtype=i32)
-        counts = self.zeros(k, dtype=i32)
-        celld = self.empty(n)
-        sums_work = self.empty(_lib.call("scrna_lloyd_sums_work_elems", k, d))
+        closest = self.empty(R, n)
+        cand_dist = self.empty(R, trials * n)
+        cums = self.empty(R, n)
+        pots = self.empty(R, 8)
+        cand = self.zeros(R, 8, dtype=i32)
+        idx = self.zeros(R, k, dtype=i32)
+        bufs = (self.zeros(R, k, ld), self.zeros(R, k, ld))   # centres of all restarts, ping-pong
+        labels = self.zeros(R, n, dtype=i32)
+        labels_old = self.zeros(R, n, dtype=i32)
+        labels_old.fill_(-1)
+        counts = self.zeros(R, k, dtype=i32)
+        celld = self.empty(R, n)
         esz = 8
         self.km_iters = 0
-        bufs = (Ca, Cb)
         # first centre of every restart: RandomState.choice(n, p=full(n, 1/n)) (SP/sklearn/cluster/_kmeans.py:231) is
         # searchsorted(cdf, u, side='right') on the sequentially accumulated cdf -- NumPy's own arithmetic, once per n
         cdf = self._uniform_cdf.get(n)
@@ -350,41 +359,50 @@ class Sc3Ops:
             cdf = np.full(n, 1.0 / n).cumsum()
             cdf /= cdf[-1]
             self._uniform_cdf = {n: cdf}
-        firsts = np.minimum(np.searchsorted(cdf, draws[: n_init * per: per], side="right"), n - 1)
-        runs_labels = self.zeros(n_init, n, dtype=i32)
-        inertias = self.zeros(n_init)
-        batch = 8   # Lloyd iterations enqueued between two polls of the device-side stop flag
-        for r in range(n_init):
-            first = int(firsts[r])
-            uptr = U.data_ptr() + (r * per + 1) * esz
-            self._call("scrna_kmeans_pp_from", X, d, n, d, xsq, k, first, uptr if k > 1 else None, trials, closest,
-                       cand_dist, cums, pots, cand, idx, state, Ca, d, self._s(), launches=4 * k + 1)
-            labels_old.fill_(-1)
-            state[6:8].zero_()
+        firsts = np.minimum(np.searchsorted(cdf, draws[: R * per: per], side="right"), n - 1)
+        # k-means++ of all restarts in one launch sequence (the restart is a grid dimension of every kernel)
+        firsts_d = t.from_numpy(firsts.astype(np.int32)).to(self.dev)
+        self._call("scrna_kmeans_pp_batched", X, ld, n, d, xsq, k, R, firsts_d, U, trials, closest, cand_dist, cums,
+                   pots, cand, idx, state, bufs[0], ld, self._s(), launches=4 * k + 1)
+        if batched:
+            bwork = self.empty(_lib.call("scrna_lloyd_batched_work_elems", int(k), int(d), R))
             queued, st = 0, None
             while queued < max_iter:
-                nb = min(batch, max_iter - queued)
+                nb = min(self.KM_POLL, max_iter - queued)
                 for b in range(nb):
                     cur, nxt = bufs[(queued + b) % 2], bufs[(queued + b + 1) % 2]
-                    self._call("scrna_lloyd_iteration", X, d, n, d, cur, nxt, d, k, labels, labels_old, counts, celld,
-                               sums_work, state, int(max_iter), self._s(), launches=5)
+                    self._call("scrna_lloyd_iteration_batched", X, ld, n, d, cur, nxt, ld, k, R, labels, labels_old,
+                               counts, celld, bwork, state, int(max_iter), self._s(), launches=6)
                 queued += nb
-                st = state.cpu().numpy()          # one poll per batch (the stop rule itself lives on the device)
-                if st[6] != 0.0:
+                st = state.cpu().numpy()              # one poll per batch: every restart's stop flag
+                if (st[:, 6] != 0.0).all():
                     break
-            done_iters = int(st[7])
+        else:
+            swork = self.empty(_lib.call("scrna_lloyd_sums_work_elems", k, d))
+            for r in range(R):
+                queued = 0
+                while queued < max_iter:
+                    nb = min(self.KM_POLL, max_iter - queued)
+                    for b in range(nb):
+                        cur, nxt = bufs[(queued + b) % 2][r], bufs[(queued + b + 1) % 2][r]
+                        self._call("scrna_lloyd_iteration", X, ld, n, d, cur, nxt, ld, k, labels[r], labels_old[r],
+                                   counts[r], celld[r], swork, state[r], int(max_iter), self._s(), launches=5)
+                    queued += nb
+                    if float(state[r, 6].cpu()) != 0.0:   # one poll per batch (the stop rule itself lives on the device)
+                        break
+            st = state.cpu().numpy()
+        for r in range(R):
+            done_iters = int(st[r, 7])
             self.km_iters += done_iters
-            cur = bufs[done_iters % 2]             # the centres the last executed iteration wrote
-            if st[6] != 1.0:                       # not strict convergence: labels of the final centres
-                self._call("scrna_lloyd_assign", X, d, n, d, cur, d, k, labels, self._s())
-            self._call("scrna_km_inertia", X, d, n, d, cur, d, labels, celld, state, self._s(), launches=2)
-            inertias[r: r + 1].copy_(state[3:4])
-            runs_labels[r].copy_(labels)
+            cur = bufs[done_iters % 2][r]           # the centres the last executed iteration of this restart wrote
+            if st[r, 6] != 1.0:                      # not strict convergence: labels of the final centres
+                self._call("scrna_lloyd_assign", X, ld, n, d, cur, ld, k, labels[r], self._s())
+            self._call("scrna_km_inertia", X, ld, n, d, cur, ld, labels[r], celld[r], state[r], self._s(), launches=2)
         # restart selection on the host from ONE read-back (sklearn _kmeans.py:1534-1541)
-        inert = inertias.cpu().numpy()
-        labs = runs_labels.cpu().numpy()
+        inert = state[:, 3].cpu().numpy()
+        labs = labels.cpu().numpy()
         best = None
-        for r in range(n_init):
+        for r in range(R):
             if best is None or (inert[r] < best[1] and not same_clustering(labs[r], best[0], k)):
                 best = (labs[r].copy(), float(inert[r]))
         return best[0]

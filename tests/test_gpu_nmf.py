@@ -42,7 +42,7 @@ def sweep_path(request, monkeypatch):
                                    (2100, 1300, 24), (900, 700, 40)])
 def test_f16_sweeps_match_fp64_products(kernels, g, n, k, parts, monkeypatch):
     """The 16-bit sweep (fp16 storage of X and X^T staged by swizzled TMA boxes straight into tcgen05.mma kind::f16,
-    three-part scaled fp16 split of the factor) on both resident copies, against fp64 products; counts up to
+    two- or three-part scaled fp16 split of the factor) on both resident copies, against fp64 products; counts up to
     fp16's exact-integer limit 2048 and factors with a wide dynamic range."""
     torch = kernels.torch
     monkeypatch.setenv("SCRNA_B200_H_PARTS", str(parts))
@@ -93,7 +93,7 @@ def test_f16_not_chosen_for_inexact_data(kernels):
 
 
 def test_update_writes_f16_operand_shadow(kernels):
-    """The epilogue's three-part fp16 shadow equals the one scrna_nmf_h_shadow builds from the master, the scales are
+    """The epilogue's fp16 operand shadow (three parts here) equals the one scrna_nmf_h_shadow builds from the master, the scales are
     local to 128-row groups (max|entry| * 2^e in [2^13, 2^14)), and the parts reconstruct every entry to max(2^-33 of
     the entry, 2^-38 of the group's largest entry): 33 significant bits, floored by fp16's subnormal spacing."""
     import scrna_b200._lib as L

@@ -227,19 +227,24 @@ def test_pairwise_row_blocks_bit_identical(ops, op):
     assert torch.equal(full, parts)
 
 
-def test_kmeans_labelings_vs_reference(ops, sc3g):
+@pytest.mark.parametrize("batched", [True, False])
+def test_kmeans_labelings_vs_reference(ops, sc3g, batched):
+    """All 15 k-means labelings of the reference's ensemble, once with every restart of a fit batched into one
+    launch set per Lloyd iteration (DMMA assignment) and once restart by restart."""
     k, pc = int(sc3g["k"]), [int(v) for v in sc3g["pc_range"]]
     V = sc3g["V_euclidean_pca"]
     np.random.seed(int(sc3g["seed"]))
     per, _ = so.kmeans_draw_count(k)
     for i, d in enumerate(range(pc[0], pc[1] + 1)):
         draws = np.random.random_sample(10 * per)
-        lab = ops.kmeans(ops.to_device(V), d, k, draws)
+        lab = ops.kmeans(ops.to_device(V), d, k, draws, batched=batched)
         np.testing.assert_array_equal(lab, sc3g["kmeans_euclid_pca"][i])
 
 
-@pytest.mark.parametrize("n,d,k", [(200, 3, 4), (513, 17, 6), (64, 40, 2), (1000, 9, 8)])
-def test_kmeans_vs_sklearn_seeded(ops, n, d, k):
+@pytest.mark.parametrize("batched", [True, False])
+@pytest.mark.parametrize("n,d,k", [(200, 3, 4), (513, 17, 6), (64, 40, 2), (1000, 9, 8), (700, 33, 11), (1500, 70, 20),
+                                   (330, 5, 1)])
+def test_kmeans_vs_sklearn_seeded(ops, n, d, k, batched):
     from sklearn.cluster import KMeans
     rng = np.random.RandomState(n + d)
     X = np.concatenate([rng.randn(n // k + 1, d) + 5 * rng.randn(1, d) for _ in range(k)])[:n]
@@ -247,15 +252,35 @@ def test_kmeans_vs_sklearn_seeded(ops, n, d, k):
     ref = KMeans(n_clusters=k, n_init=10, max_iter=10000, init='k-means++').fit_predict(X)
     np.random.seed(n)
     per, _ = so.kmeans_draw_count(k)
-    got = ops.kmeans(ops.to_device(X), d, k, np.random.random_sample(10 * per))
+    got = ops.kmeans(ops.to_device(X), d, k, np.random.random_sample(10 * per), batched=batched)
     np.testing.assert_array_equal(got, ref)
 
 
-def test_kmeans_duplicate_points_empty_cluster(ops):
+def test_kmeans_batched_limits(ops):
+    """k above the batched kernels' 48 columns runs restart by restart; asking for the batched path there raises."""
+    rng = np.random.RandomState(2)
+    X = rng.randn(400, 6)
+    per, _ = so.kmeans_draw_count(60)
+    draws = rng.random_sample(10 * per)
+    lab = ops.kmeans(ops.to_device(X), 6, 60, draws)
+    assert lab.shape == (400,) and len(np.unique(lab)) > 30
+    with pytest.raises(ValueError):
+        ops.kmeans(ops.to_device(X), 6, 60, draws, batched=True)
+    # 3 restarts, max_iter 1 and 2: the stop flag of max_iter and the final assignment
+    per, _ = so.kmeans_draw_count(5)
+    draws = rng.random_sample(3 * per)
+    for mi in (1, 2, 7):
+        a = ops.kmeans(ops.to_device(X), 6, 5, draws, n_init=3, max_iter=mi, batched=True)
+        b = ops.kmeans(ops.to_device(X), 6, 5, draws, n_init=3, max_iter=mi, batched=False)
+        np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("batched", [True, False])
+def test_kmeans_duplicate_points_empty_cluster(ops, batched):
     """Duplicate points force empty clusters: the relocation path must run and produce a valid labeling."""
     X = np.repeat(np.array([[0.0, 0.0], [1.0, 1.0], [5.0, 5.0]]), 10, axis=0)
     per, _ = so.kmeans_draw_count(5)
-    lab = ops.kmeans(ops.to_device(X), 2, 5, np.random.RandomState(0).random_sample(10 * per))
+    lab = ops.kmeans(ops.to_device(X), 2, 5, np.random.RandomState(0).random_sample(10 * per), batched=batched)
     assert lab.shape == (30,) and lab.min() >= 0 and lab.max() < 5
     for blk in range(3):   # identical points share a label unless a relocation split one off
         assert len(set(lab[blk * 10:(blk + 1) * 10].tolist())) <= 3
