@@ -71,13 +71,15 @@ class SC3Clustering(AbstractClustering):
         dists = []
         for d in self.dists_list:
             if own_dimred and _impl.is_own(d, _impl.distances):
-                dists.append(d(X, self.gene_ids[self.remain_gene_inds], _device=True))
+                # with a comm: row blocks of the distance matrix / of the Gram / of the back-transformed vectors
+                # are computed by different ranks and all-gathered (every rank ends with identical matrices)
+                dists.append(d(X, self.gene_ids[self.remain_gene_inds], _device=True, _comm=self.comm))
             else:
                 dists.append(d(X, self.gene_ids[self.remain_gene_inds]))
         transf = []
         for d in dists:
             for t in self.dimred_list:
-                transf.append(t(d, _device=True) if own_dimred else t(d))
+                transf.append(t(d, _device=True, _comm=self.comm) if own_dimred else t(d))
 
         range_inds = list(range(self.pc_range[0], self.pc_range[1] + 1))
         if self.sub_sample and len(range_inds) > 15:
@@ -133,7 +135,10 @@ class SC3Clustering(AbstractClustering):
                 consensus2 = _impl._remember(C.cpu().numpy(), C)
         else:
             consensus2 /= cnt
-        self.cluster_labels, self.dists = self.consensus_clustering(consensus2)
+        if self.comm is not None and _impl.is_own(self.consensus_clustering, _impl.consensus_clustering):
+            self.cluster_labels, self.dists = self.consensus_clustering(consensus2, _comm=self.comm)
+        else:
+            self.cluster_labels, self.dists = self.consensus_clustering(consensus2)
 
     def _gather_labels(self, fits, n):
         """All-reduce (sum) of an (n_fits x cells) label table in which every rank filled the rows it owns."""

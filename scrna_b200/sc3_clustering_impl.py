@@ -139,11 +139,11 @@ def is_own(fn, target):
     return getattr(fn, "func", fn) is target
 
 
-def distances(data, gene_ids, metric='euclidean', _device=False):
+def distances(data, gene_ids, metric='euclidean', _device=False, _comm=None):
     """cells x cells distance matrix of a transcripts x cells matrix (scRNA/sc3_clustering_impl.py:106-132):
     'euclidean' (bit-identical to scipy pdist), 'pearson' (1 - corrcoef), 'spearman' (1 - rank corrcoef)."""
     ops = _ops()
-    D = ops.distances(np.asarray(data, dtype=np.float64), metric)
+    D = ops.distances(np.asarray(data, dtype=np.float64), metric, comm=_comm)
     if _device:
         return DeviceResult(D)
     return _remember(D.cpu().numpy(), D)
@@ -174,7 +174,7 @@ def da_nmf_distances(data, gene_ids, da_model, reject_ratio=0., metric='euclidea
     return mixture * (dist2 * scale) + (1. - mixture) * dist1
 
 
-def transformations(dm, components=5, method='pca', _device=False):
+def transformations(dm, components=5, method='pca', _device=False, _comm=None):
     """(cells x cells matrix rebuilt from the kept components, cells x components right singular vectors)
     of the PCA-scaled or 'spectral' distance matrix (scRNA/sc3_clustering_impl.py:135-203).  The first return
     value is what the reference computes and its only caller discards (sc3_clustering.py:77,95); this package's
@@ -184,7 +184,7 @@ def transformations(dm, components=5, method='pca', _device=False):
     D = dev if dev is not None else ops.to_device(np.asarray(dm, dtype=np.float64))
     num_cells = D.shape[0]
     M = ops.transform_matrix(D, method)
-    V, vals = ops.right_singular_vectors(M, components)
+    V, vals = ops.right_singular_vectors(M, components, comm=_comm)
     vecs = V.cpu().numpy()
     if _device:
         return None, _remember(vecs, V)
@@ -245,11 +245,11 @@ def build_consensus_matrix(X):
     return _remember(C.cpu().numpy(), C)
 
 
-def consensus_clustering(consensus, n_components=5):
+def consensus_clustering(consensus, n_components=5, _comm=None):
     """(labels, cells x cells Euclidean distances between consensus rows): pdist -> complete linkage ->
     cut_tree(n_components) (scRNA/sc3_clustering_impl.py:244-260)."""
     ops = _ops()
     dev = _device_of(consensus)
     C = dev if dev is not None else ops.to_device(np.asarray(consensus, dtype=np.float64))
-    labels, D, _ = ops.consensus_clustering(C, n_components)
+    labels, D, _ = ops.consensus_clustering(C, n_components, comm=_comm)
     return labels, D.cpu().numpy()

@@ -147,7 +147,7 @@ class Sc3Ops:
 
     EIGH_MIN_N = 6000    # from here on the tridiagonalisation solver replaces the Jacobi sweeps (16 x 4 n^3 FMA)
 
-    def right_singular_vectors(self, M, components, max_sweeps=40, tol=1e-15, blocked=None, method="auto"):
+    def right_singular_vectors(self, M, components, max_sweeps=40, tol=1e-15, blocked=None, method="auto", comm=None):
         """First `components` right singular vectors of the n x n device matrix M (descending singular
         values); returns (V device n x components, singular values numpy n).
         method 'jacobi': one-sided Jacobi on M itself -- n > 64 the block algorithm (sc3_svd_block.cu: GEMM-shaped,
@@ -162,7 +162,7 @@ class Sc3Ops:
             raise ValueError("method must be 'auto', 'jacobi' or 'eigh'")
         if method == "eigh" or (method == "auto" and blocked is None and n >= self.EIGH_MIN_N):
             with self._stage("svd"):
-                return self._rsv_eigh(M, components)
+                return self._rsv_eigh(M, components, comm)
         if blocked is None:
             blocked = n > 64
         if blocked:
@@ -228,7 +228,7 @@ class Sc3Ops:
         self._last = (W, od, inv[order[:c]], vals[order][:c])   # for rebuilt_matrix()
         return V, vals[order]
 
-    def _rsv_eigh(self, M, components):
+    def _rsv_eigh(self, M, components, comm=None):
         """Leading `components` eigenpairs of A = M^T M (sc3_eigh.cu).  The host does O(n) bookkeeping only:
         Gershgorin bounds of the tridiagonal matrix and dstein's separation of numerically coincident eigenvalues."""
         t = self.torch
@@ -238,7 +238,7 @@ class Sc3Ops:
             raise ValueError("eigh path needs n >= 3 and components <= n")
         A = self.empty(n, n)
         with self._stage("svd.gram"):
-            self._call("scrna_pairwise_f64", M, n, n, n, 1, A, n, self._s())                 # A = M^T M
+            self._pairwise(M, n, n, 1, A, comm)                                             # A = M^T M (row blocks over the ranks)
         d, e, tau = self.empty(n), self.zeros(n), self.empty(n)
         work = self.empty(_lib.call("scrna_sytrd_work_elems", n))
         with self._stage("svd.tridiagonalise"):
@@ -275,7 +275,15 @@ class Sc3Ops:
         ZT = self.empty(c, n)
         self._call("scrna_transpose_f64", X, c, n, c, ZT, n, self._s())
         with self._stage("svd.back_transform"):
-            self._call("scrna_ormtr_f64", A, n, n, tau, ZT, c, self._s())
+            if comm is None or comm.world <= 1:
+                self._call("scrna_ormtr_f64", A, n, n, tau, ZT, c, self._s())
+            else:   # the vectors are independent: each rank back-transforms a block of them, then all-gather
+                from .nmf_solver import shard_bounds
+                bounds = [shard_bounds(c, comm.world, r) for r in range(comm.world)]
+                c0, c1 = bounds[comm.rank]
+                if c1 > c0:
+                    self._call("scrna_ormtr_f64", A, n, n, tau, ZT[c0:c1], c1 - c0, self._s())
+                comm.all_gather_rows(ZT, bounds)
         V = X
         self._call("scrna_transpose_f64", ZT, n, c, n, V, c, self._s())
         vals = np.zeros(n)
@@ -425,7 +433,7 @@ class Sc3Ops:
         self._call("scrna_consensus_scale", M, n, n, float(cnt), C, n, self._s())
         return C
 
-    def consensus_clustering(self, C, n_clusters):
+    def consensus_clustering(self, C, n_clusters, comm=None):
         """pdist(C) -> complete linkage -> cut_tree(n_clusters).  Returns (labels numpy int64, device n x n
         row-distance matrix, linkage matrix Z numpy (n-1) x 4)."""
         t = self.torch
@@ -433,7 +441,7 @@ class Sc3Ops:
         n = C.shape[0]
         D = self.empty(n, n)
         with self._stage("consensus_row_distances"):
-            self._call("scrna_pairwise_f64", C, n, n, n, 0, D, n, self._s())
+            self._pairwise(C, n, n, 0, D, comm)
         with self._stage("linkage"):
             return self._linkage(D, n, n_clusters)
 
