@@ -53,10 +53,19 @@ class AbstractClustering(object):
         # data[:, keep_cells][keep_genes, :] as the reference, minus the fancy-index passes that select everything
         # (two gather copies of a 3.2 GB matrix at 20 000 x 20 000); the result is always a fresh array
         a = data if keep_cells.size == n_cells else data[:, keep_cells]
-        if keep_genes.size == n_genes:
-            sliced = a.copy() if a is data else a
-        else:
+        if keep_genes.size != n_genes:
             sliced = a[keep_genes, :]
+        elif a is not data:
+            sliced = a
+        elif self.data_transf is _identity:
+            # nothing filtered, nothing transformed: pp_data is a READ-ONLY view of the private copy the constructor
+            # made (same values as the reference's fresh array; a write raises instead of touching `data`) -- the
+            # copy is 3.2 GB of freshly faulted pages (2-3 s) at 20 000 x 20 000
+            sliced = data.view()
+            sliced.flags.writeable = False
+            return sliced, keep_genes, keep_cells
+        else:
+            sliced = a.copy()          # a user transformation may work in place
         return self.data_transf(sliced), keep_genes, keep_cells
 
     def apply(self):

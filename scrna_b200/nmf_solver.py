@@ -56,6 +56,17 @@ def shard_bounds(n_total, world, rank):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def _from_numpy(torch, a):
+    """torch.from_numpy without the "array is not writable" warning: read-only views (pp_data of a pass-through
+    pre-processing, remembered stage results) are only ever read."""
+    if a.flags.writeable:
+        return torch.from_numpy(a)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        return torch.from_numpy(a)
+
+
 class DeviceMatrix:
     """X shard: genes x cells, row-major fp32 on the device, leading dimension padded to 32 cells
     (128 B) and zero-filled beyond the real cells."""
@@ -91,12 +102,12 @@ class DeviceMatrix:
             arr = np.ascontiguousarray(arr, dtype=np.float64) if arr.dtype != np.float32 else arr
         if arr.dtype == np.float32:
             out.zero_()
-            out[:, :n].copy_(torch.from_numpy(np.ascontiguousarray(arr)), non_blocking=False)
+            out[:, :n].copy_(_from_numpy(torch, np.ascontiguousarray(arr)), non_blocking=False)
             return cls(out, n)
         rows_per_band = max(1, int(band_bytes // max(1, n * 8)))
         for r0 in range(0, g, rows_per_band):
             r1 = min(g, r0 + rows_per_band)
-            band = torch.from_numpy(np.ascontiguousarray(arr[r0:r1])).to(dev)
+            band = _from_numpy(torch, np.ascontiguousarray(arr[r0:r1])).to(dev)
             kernels.convert_pad(band, n, out[r0:r1], ldx, r1 - r0, n)
         if out.is_cuda:
             torch.cuda.current_stream().synchronize()

@@ -71,7 +71,13 @@ class Sc3Ops:
         t = self.torch
         if isinstance(a, t.Tensor):
             return a
-        return t.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.dev)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if not a.flags.writeable:              # read-only stage results / pp_data views: torch warns, nothing is written
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", UserWarning)
+                return t.from_numpy(a).to(self.dev)
+        return t.from_numpy(a).to(self.dev)
 
     def empty(self, *shape, dtype=None):
         t = self.torch

@@ -36,12 +36,12 @@ def run(comm):
     ops = sc._ops()
     ops.stage_seconds = {}
     torch.cuda.synchronize()
-    if world > 1:
+    if comm is not None:
         dist.barrier()
     t0 = time.perf_counter()
     s3.apply()
     torch.cuda.synchronize()
-    if world > 1:
+    if comm is not None:
         dist.barrier()
     dt = time.perf_counter() - t0
     st = {a: round(b, 4) for a, b in ops.stage_seconds.items()}
