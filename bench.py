@@ -343,15 +343,9 @@ def sc3_consensus_seconds(cells, genes, k=8):
     np.random.seed(0)
     pc = [max(1, int(np.floor(0.04 * cells))), int(np.ceil(0.07 * cells))]
     s3 = SC3Clustering(X, np.arange(genes), pc_range=pc, sub_sample=True, consensus_mode=0)
-    kept = {}
-
-    def dimred(D):
-        out = sc.transformations(D, components=pc[1], method="pca")
-        kept["vecs"] = out[1]
-        return out
-
+    # the reference's own wiring (cmd_target.py:220-242): functools.partial objects of the sc3_clustering_impl callables
     s3.add_distance_calculation(partial(sc.distances, metric="euclidean"))
-    s3.add_dimred_calculation(dimred)
+    s3.add_dimred_calculation(partial(sc.transformations, components=pc[1], method="pca"))
     s3.add_intermediate_clustering(partial(sc.intermediate_kmeans_clustering, k=k))
     s3.set_build_consensus_matrix(sc.build_consensus_matrix)
     s3.set_consensus_clustering(partial(sc.consensus_clustering, n_components=k))
@@ -367,7 +361,8 @@ def sc3_consensus_seconds(cells, genes, k=8):
     # in the first k - 1 directions; SC3's rule (sc3_clustering.py:82-85 with cmd_target.py:220-238) instead
     # clusters on d in [0.04 n, 0.07 n] = 800..1400 dimensions at this size, nearly all of them noise, which is what
     # pulls the consensus ARI down as n grows (profiles/r02_sc3_ari_vs_cells.json) -- the vectors themselves are fine.
-    lead = np.ascontiguousarray(kept["vecs"][:, :k])
+    W_, od_, inv_, _ = ops._last          # rows od_[r] of W_ times inv_[r] = the r-th right singular vector
+    lead = np.ascontiguousarray((W_[od_[:k].long()].cpu().numpy() * np.asarray(inv_)[:k, None]).T)
     ari_lead = float(adjusted_rand_score(lab, np.asarray(sc.intermediate_kmeans_clustering(lead, k=k)).ravel()))
     fp64_peak = 37.0e12          # B200 FP64 (DFMA or DMMA) flop/s: 18.5 TFMA/s measured, profiles/r01_dmma_rate_microbench.txt
     n = float(cells)
@@ -384,7 +379,8 @@ def sc3_consensus_seconds(cells, genes, k=8):
             "jacobi_sweeps": ops.jacobi_sweeps, "dims": 15 if pc[1] - pc[0] + 1 > 15 else pc[1] - pc[0] + 1,
             "ari_vs_simulated_labels": float(adjusted_rand_score(lab, s3.cluster_labels)),
             "ari_kmeans_on_leading_k_vectors_only": ari_lead,
-            "through": "SC3Clustering.apply() (class API, NumPy at every plug-in boundary)",
+            "through": "SC3Clustering.apply() (class API with the reference's partial(sc3_clustering_impl.*) wiring; "
+                       "the package's own stages hand each other device tensors, foreign callables would get NumPy)",
             "config": "1 distance (euclidean) x 1 transformation (pca), n_init=10: cmd_target.py defaults "
                       "(BASELINE.json configs[3])"}
 
