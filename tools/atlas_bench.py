@@ -48,11 +48,21 @@ def main():
     if world > 1:
         dist.all_reduce(xsum)
     xmean = float(xsum.item()) / (float(g) * n)
-    rng = np.random.RandomState(0)
-    avg = np.sqrt(xmean / k)
-    G0 = avg * np.abs(rng.standard_normal((g, k)))
-    C0 = avg * np.abs(np.random.RandomState(1 + rank).standard_normal((k, n_loc)))
-    slv = NmfSolver(dm, k, kernels=kn, comm=comm)
+    # NNDSVDar on the device over the cell shards (scrna_b200/nmf_init.py: what NmfClustering.apply(comm=,
+    # cells='sharded') runs): the randomized-SVD passes are sweeps over the shards, the host factorisations replicated
+    from scrna_b200.nmf_init import nndsvdar_init_device
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    G0, H0, XT = nndsvdar_init_device(dm, k, kn, seed=0, comm=comm, cell_range=(c0, c1, n) if world > 1 else None)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    init_s = time.perf_counter() - t0
+    C0 = np.ascontiguousarray(H0[:, c0:c1]) if H0.shape[1] == n and world > 1 else H0
+    del H0
+    slv = NmfSolver(dm, k, kernels=kn, comm=comm, XT=XT)
     slv.prepare(G0, C0, solver="mu", l1_G=bench.L1, l2_G=bench.L2, l1_C=bench.L1, l2_C=bench.L2, tol=0.0,
                 max_iter=10 ** 9)
 
@@ -84,9 +94,12 @@ def main():
     G = slv.G64[:k, :g].cpu().numpy().T.copy()
     out = {"workload": "NMF MU %d genes x %d cells k=%d on %d GPU(s) (BASELINE configs[4])" % (g, n, k, world),
            "iterations_per_s": args.steps / (ms / 1e3), "ms_per_iteration": ms / args.steps,
-           "sweep_kernel": "tcgen05 kp=%d%s" % (slv.kp, " (TF32-exact X)" if slv.tc_flags else "") if slv.tc else "fp32",
+           "init": "NNDSVDar on the device, cells sharded (nndsvdar_init_device with comm)", "init_seconds": init_s,
+           "sweep_kernel": ("tcgen05 kind::f16, fp16 storage, kq=%d" % slv.kp if slv.half else
+                            "tcgen05 3xTF32 kp=%d%s" % (slv.kp, " (TF32-exact X)" if slv.tc_flags else "") if slv.tc
+                            else "fp32"),
            "sweep_ms_per_gpu": sweep_ms, "sweep_gbs_per_gpu": sweep_gbs,
-           "x_bytes_per_gpu": int(g) * dm.ldx * 4, "frobenius_error_after": err}
+           "x_bytes_per_gpu": int(g) * dm.ldx * (2 if slv.half else 4), "frobenius_error_after": err}
     del slv, dm, Xd
     torch.cuda.empty_cache()
     if rank == 0:
