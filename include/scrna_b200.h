@@ -287,6 +287,12 @@ int scrna_argmax_cols(const double* H64, int k, int64_t ncols, int64_t ldc, int3
 int scrna_mix_gather(const float* X, int64_t ldx, int g, int64_t ncols, const double* G64, int kp,
                      const int32_t* labels, double mix, double* mixed64, int64_t ld64, float* mixed32,
                      int64_t ld32, double* newtrg64, void* stream);
+/* The same with the dense H instead of the one-hot H2 (get_mixed_data(use_H2=False), nmf_clustering.py:180-184):
+ * mixed64 = mix . (W.H) + (1 - mix) . X and / or newtrg64 = W.H, both g x ld64 fp64; G64: g x kp row-major,
+ * H64: kp x ldc component-major. */
+int scrna_mix_dense(const float* X, int64_t ldx, int g, int64_t ncols, const double* G64, int k, int kp,
+                    const double* H64, int64_t ldc, double mix, double* mixed64, int64_t ld64, double* newtrg64,
+                    void* stream);
 
 /* Per-cell rejection statistics in one sweep (nmf_clustering.py:236-271): out is 5 x ldo fp64:
  * column sums of X, L1 and squared-L2 residuals against W.H, then against W.H2. */

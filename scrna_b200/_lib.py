@@ -79,6 +79,7 @@ _SIGNATURES = {
     "scrna_argmax_cols": [c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr],
     "scrna_mix_gather": [c_ptr, c_i64, c_int, c_i64, c_ptr, c_int, c_ptr, c_dbl, c_ptr, c_i64, c_ptr, c_i64,
                          c_ptr, c_ptr],
+    "scrna_mix_dense": [c_ptr, c_i64, c_int, c_i64, c_ptr, c_int, c_int, c_ptr, c_i64, c_dbl, c_ptr, c_i64, c_ptr, c_ptr],
     "scrna_reject_stats": [c_ptr, c_i64, c_int, c_i64, c_ptr, c_int, c_int, c_ptr, c_i64, c_ptr, c_ptr, c_i64,
                            c_ptr],
     # ---- SC3 ----

@@ -405,6 +405,53 @@ extern "C" int scrna_argmax_cols(const double* H64, int k, int64_t ncols, int64_
   return last_launch_status();
 }
 
+// mix . (W.H) + (1 - mix) . X with the dense H (get_mixed_data(use_H2=False), nmf_clustering.py:180-184): four cells per
+// thread, the k-term dot product of each (gene, cell) in component order, W.H never kept beyond the optional output.
+__global__ void __launch_bounds__(256)
+mix_dense_kernel(const float* __restrict__ X, int64_t ldx, int g, int64_t ncols, const double* __restrict__ G64, int k,
+                 int kp, const double* __restrict__ H64, int64_t ldc, double mix, double* __restrict__ mixed64,
+                 int64_t ld64, double* __restrict__ newtrg64) {
+  const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j >= ncols) return;
+  for (int i = blockIdx.y; i < g; i += gridDim.y) {
+    const float4 x = ld_stream(reinterpret_cast<const float4*>(X + (int64_t)i * ldx + j));
+    const float xv[4] = {x.x, x.y, x.z, x.w};
+    const double* wrow = G64 + (int64_t)i * kp;
+    double w[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = 0; t < k; ++t) {
+      const double wt = wrow[t];
+      const double* h = H64 + (int64_t)t * ldc + j;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (j + c < ncols) w[c] = fma(wt, h[c], w[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (j + c < ncols) {
+        if (mixed64) mixed64[(int64_t)i * ld64 + j + c] = mix * w[c] + (1.0 - mix) * (double)xv[c];
+        if (newtrg64) newtrg64[(int64_t)i * ld64 + j + c] = w[c];
+      }
+    }
+  }
+}
+
+extern "C" int scrna_mix_dense(const float* X, int64_t ldx, int g, int64_t ncols, const double* G64, int k, int kp,
+                               const double* H64, int64_t ldc, double mix, double* mixed64, int64_t ld64,
+                               double* newtrg64, void* stream) {
+  if (!X || !G64 || !H64 || g <= 0 || ncols <= 0 || k <= 0 || k > kp || (ldx & 3) || ncols > ldx || ncols > ldc ||
+      (!mixed64 && !newtrg64) || ld64 < ncols)
+    return SCRNA_ERR_BADARG;
+  const int64_t quads = ceil_div(ncols, 4);
+  int gy = (int)((int64_t)num_sms() * 8 / (ceil_div(quads, 256)));
+  if (gy < 1) gy = 1;
+  if (gy > g) gy = g;
+  if (gy > 65535) gy = 65535;
+  dim3 grid((unsigned)ceil_div(quads, 256), (unsigned)gy);
+  mix_dense_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, g, ncols, G64, k, kp, H64, ldc, mix, mixed64, ld64,
+                                                          newtrg64);
+  return last_launch_status();
+}
+
 extern "C" int scrna_mix_gather(const float* X, int64_t ldx, int g, int64_t ncols, const double* G64, int kp,
                                 const int32_t* labels, double mix, double* mixed64, int64_t ld64,
                                 float* mixed32, int64_t ld32, double* newtrg64, void* stream) {

@@ -211,6 +211,11 @@ class CudaKernels:
         self._call("scrna_mix_gather", X, ldx, g, ncols, G64, kp, labels, float(mix), mixed64, ld64, mixed32, ld32,
                    newtrg64, self._s())
 
+    def mix_dense(self, X, ldx, g, ncols, G64, k, kp, H64, ldc, mix, mixed64, ld64, newtrg64):
+        self.launches += 1
+        self._call("scrna_mix_dense", X, ldx, g, ncols, G64, k, kp, H64, ldc, float(mix), mixed64, ld64, newtrg64,
+                   self._s())
+
     def reject_stats(self, X, ldx, g, ncols, G64, k, kp, H64, ldc, labels, out, ldo):
         self._call("scrna_reject_stats", X, ldx, g, ncols, G64, k, kp, H64, ldc, labels, out, ldo, self._s())
 

@@ -340,8 +340,8 @@ class DaNmfClustering(NmfClustering):
             mixed_data, new_trg_data = sess.mixed(mix)
             mixed_data, new_trg_data = part.gather(mixed_data, kn), part.gather(new_trg_data, kn)
         else:
-            new_trg_data = W.dot(H)
-            mixed_data = mix * new_trg_data + (1. - mix) * trg_data
+            mixed_data, new_trg_data = sess.mixed_dense(mix)      # mix . (W.H) + (1 - mix) . X on the device
+            mixed_data, new_trg_data = part.gather(mixed_data, kn), part.gather(new_trg_data, kn)
         if np.any(trg_data < 0.0):
             print('Error! Negative values in target data!')
         if np.any(mixed_data < 0.0):

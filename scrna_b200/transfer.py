@@ -138,6 +138,16 @@ class TransferSession:
             out.append(DeviceMatrix(m32, X.n))
         return tuple(out)
 
+    def mixed_dense(self, mix):
+        """(mix . W.H + (1 - mix) . X, W.H) as fp64 host arrays: get_mixed_data(use_H2=False)."""
+        t, X = self.torch, self.X
+        dev = X.data.device
+        mixed64 = t.empty((X.g, X.n), dtype=t.float64, device=dev)
+        newtrg = t.empty((X.g, X.n), dtype=t.float64, device=dev)
+        self.kn.mix_dense(X.data, X.ldx, X.g, X.n, self.G64, self.k, self.kp, self.H64, self.ldc, mix, mixed64, X.n,
+                          newtrg)
+        return mixed64.cpu().numpy(), newtrg.cpu().numpy()
+
     def reject_stats(self):
         """5 x n_t: column sums, L1 / squared-L2 residuals vs W.H, then vs W.H2."""
         t, X = self.torch, self.X

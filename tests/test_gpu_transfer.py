@@ -48,6 +48,22 @@ def test_get_mixed_data_vs_golden(kernels, default_sim, golden):
         assert np.linalg.norm(v - ref) <= 2e-3 * max(np.linalg.norm(ref), 1e-12), name
 
 
+def test_get_mixed_data_with_dense_H_on_the_device(kernels, default_sim, golden):
+    """get_mixed_data(use_H2=False) (nmf_clustering.py:180-184): mix . (W.H) + (1 - mix) . X from the device kernel
+    (scrna_mix_dense), against the same expression in NumPy with the session's own W and H."""
+    from scrna_b200 import DaNmfClustering
+    src = _Src(golden("nmf_source")["initw_dictionary"], np.arange(1000), 7)
+    da = DaNmfClustering(src, default_sim["trg"].copy(), np.arange(1000), 7)
+    np.random.seed(1)
+    launches0 = kernels.launches
+    mixed, new_trg, trg = da.get_mixed_data(mix=0.3, use_H2=False)
+    assert kernels.launches > launches0
+    W, H = da.intermediate_model[0], da.intermediate_model[1]
+    ref_new = W.dot(H)
+    np.testing.assert_allclose(new_trg, ref_new, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(mixed, 0.3 * ref_new + 0.7 * trg, rtol=1e-12, atol=1e-12)
+
+
 def test_danmf_apply_vs_golden(kernels, default_sim, golden):
     from scrna_b200 import DaNmfClustering
     g = golden("transfer")
