@@ -52,6 +52,7 @@ eh_col_kernel(const double* __restrict__ A, int64_t ld, int n, int c, int i, con
   double ss = 0.0;
   for (int r = c + blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
     double v = A[(int64_t)c * ld + r];
+#pragma unroll 8
     for (int p = 0; p < i; ++p) v -= Vp[(int64_t)p * n + r] * wc[p] + Wp[(int64_t)p * n + r] * vc[p];
     if (r == c) d[c] = v;
     else {
@@ -150,23 +151,29 @@ eh_symv_upper_kernel(const double* __restrict__ A, int64_t ld, int n, int c, con
     cok[q] = s >= lo && s < n;
   }
   double* pr = PR + (int64_t)(J - b0) * n;
-#pragma unroll 4
-  for (int rr = 0; rr < 16; ++rr) {
-    const int rl = warp * 16 + rr, r = I0 + rl;
-    if (r < lo || r >= n) continue;                       // uniform over the warp
-    const double* row = A + (int64_t)r * ld + J0 + lane;
-    double av[4];
+  for (int rb = 0; rb < 16; rb += 4) {                   // four rows = sixteen loads per thread in flight
+    double av[4][4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) av[q] = cok[q] ? row[32 * q] : 0.0;
-    const double vi = vI[rl];
-    double rs = 0.0;
+    for (int u = 0; u < 4; ++u) {
+      const int r = I0 + warp * 16 + rb + u;
+      const bool rok = r >= lo && r < n;                 // uniform over the warp
+      const double* row = A + (int64_t)(rok ? r : lo) * ld + J0 + lane;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      rs = fma(av[q], vj[q], rs);
-      cacc[q] = fma(av[q], vi, cacc[q]);
+      for (int q = 0; q < 4; ++q) av[u][q] = (rok && cok[q]) ? row[32 * q] : 0.0;
     }
-    rs = warp_sum(rs);
-    if (lane == 0) pr[r] = rs;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int rl = warp * 16 + rb + u, r = I0 + rl;
+      const double vi = vI[rl];
+      double rs = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        rs = fma(av[u][q], vj[q], rs);
+        cacc[q] = fma(av[u][q], vi, cacc[q]);
+      }
+      rs = warp_sum(rs);
+      if (lane == 0 && r >= lo && r < n) pr[r] = rs;
+    }
   }
   if (offdiag) {
 #pragma unroll
@@ -223,6 +230,9 @@ eh_panel_dots_kernel(int n, int c, int i, double* __restrict__ Vp, const double*
 }
 
 // ---- k5: w' = y - Vp^T t1 - Wp^T t2 ; partial w'.v ------------------------------------------------------------------
+// Eight threads per row: thread `sub` of a row sums the slabs (and the panel corrections) with index = sub mod 8, the
+// eight partial sums are combined by shuffles in a fixed order -- the ~150 slab reads of a row at n = 20 000 are
+// spread over eight independent chains in eight threads instead of one latency-bound chain.
 __global__ void __launch_bounds__(256)
 eh_w_kernel(int n, int c, int i, const double* __restrict__ Vp, const double* __restrict__ Wp,
             const double* __restrict__ dots_part, int nparts, const double* __restrict__ y,
@@ -239,19 +249,33 @@ eh_w_kernel(int n, int c, int i, const double* __restrict__ Vp, const double* __
   const double* vi = Vp + (int64_t)i * n;
   double dot = 0.0;
   const int b0 = (c + 1) / EH_SB, B = (n - 1) / EH_SB;
-  for (int r = c + 1 + blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
-    double v;
-    if (PR) {   // y[r] from the slabs of eh_symv_upper_kernel: tiles (I(r), J >= I(r)), then tiles (I < I(r), I(r))
-      const int Ir = r / EH_SB;
-      v = 0.0;
-      for (int J = Ir; J <= B; ++J) v += PR[(int64_t)(J - b0) * n + r];
-      for (int I = b0; I < Ir; ++I) v += PC[(int64_t)(I - b0) * n + r];
-    } else {
-      v = y[r];
+  const int sub = threadIdx.x & 7, rows_per_cta = blockDim.x >> 3;
+  for (int r0 = c + 1 + blockIdx.x * rows_per_cta; r0 < n; r0 += gridDim.x * rows_per_cta) {   // uniform per CTA
+    const int r = r0 + (threadIdx.x >> 3);
+    const bool ok = r < n;
+    double v = 0.0;
+    if (ok) {
+      if (PR) {   // y[r] from the slabs of eh_symv_upper_kernel: tiles (I(r), J >= I(r)), then tiles (I < I(r), I(r))
+        const int Ir = r / EH_SB;
+        const double* pr = PR + (int64_t)(Ir - b0) * n + r;
+        const int nr = B - Ir + 1;
+        for (int q = sub; q < nr; q += 8) v += pr[(int64_t)q * n];
+        const double* pc = PC + r;
+        const int nc = Ir - b0;
+        for (int q = sub; q < nc; q += 8) v += pc[(int64_t)q * n];
+      } else if (sub == 0) {
+        v = y[r];
+      }
+      for (int p = sub; p < i; p += 8) v -= Vp[(int64_t)p * n + r] * t1[p] + Wp[(int64_t)p * n + r] * t2[p];
     }
-    for (int p = 0; p < i; ++p) v -= Vp[(int64_t)p * n + r] * t1[p] + Wp[(int64_t)p * n + r] * t2[p];
-    w[r] = v;
-    dot = fma(v, vi[r], dot);
+    // fixed-order combination of the eight partials of the row (lanes 8a .. 8a+7 of the warp)
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (ok && sub == 0) {
+      w[r] = v;
+      dot = fma(v, vi[r], dot);
+    }
   }
   const double b = block_sum(dot, scratch);
   if (threadIdx.x == 0) part[blockIdx.x] = b;
@@ -610,9 +634,9 @@ extern "C" int scrna_sytrd_f64(double* A, int64_t ld, int n, double* d, double* 
     for (int i = 0; i < nb; ++i) {
       const int c = j + i;
       const int m = n - c;
-      int blocks = (m + 255) / 256;
+      int blocks = (m + 127) / 128;            // 128-thread CTAs: twice the CTAs of these latency-bound row kernels
       if (blocks > EH_RED) blocks = EH_RED;
-      eh_col_kernel<<<blocks, 256, 0, st>>>(A, ld, n, c, i, Vp, Wp, x, part, d, scal);
+      eh_col_kernel<<<blocks, 128, 0, st>>>(A, ld, n, c, i, Vp, Wp, x, part, d, scal);
       eh_house_kernel<<<1, 32, 0, st>>>(part, blocks, c, e, tau, scal);
       {
         const int64_t T = (n - 1) / EH_SB - (c + 1) / EH_SB + 1;
@@ -621,8 +645,10 @@ extern "C" int scrna_sytrd_f64(double* A, int64_t ld, int n, double* d, double* 
       int vb = (n + 255) / 256;
       if (vb > EH_RED) vb = EH_RED;
       eh_panel_dots_kernel<<<vb, 256, 0, st>>>(n, c, i, Vp, Wp, x, scal, A + (int64_t)c * ld, dpart);
-      eh_w_kernel<<<blocks, 256, 0, st>>>(n, c, i, Vp, Wp, dpart, vb, y, PR, PC, w, part2);
-      eh_wfin_kernel<<<vb, 256, 0, st>>>(n, c, i, Vp, Wp, w, part2, blocks, scal);
+      int wblocks = (m + 31) / 32;             // 32 rows x 8 threads per CTA
+      if (wblocks > EH_RED) wblocks = EH_RED;
+      eh_w_kernel<<<wblocks, 256, 0, st>>>(n, c, i, Vp, Wp, dpart, vb, y, PR, PC, w, part2);
+      eh_wfin_kernel<<<vb, 256, 0, st>>>(n, c, i, Vp, Wp, w, part2, wblocks, scal);
     }
     const int lo = j + nb;
     if (lo < n) {
