@@ -486,16 +486,19 @@ extern "C" int scrna_nmf_wtx_h_splits(int g, int64_t ncols, int kq, int parts) {
   int max_split = g / 512;
   if (max_split > 64) max_split = 64;
   if (max_split < 1) max_split = 1;
+  // Time model of a sweep: CTAs run one per SM in waves, a CTA costs its row span plus a fixed part (pipeline fill,
+  // tensor-memory allocation, last drain, partial write) worth ~700 rows of streaming (measured on the 12 500-cell
+  // shard of the 8-GPU run: 5 splits x 25 tiles beat 11 x 25, profiles/r02_split_counts_shard_12500.txt).
   int best = 1;
-  double best_score = -1.0;
+  double best_cost = 1e300;
   for (int s = 1; s <= max_split; ++s) {
     const int rps = h_rows_per_split(g, s);
     if ((int)ceil_div(g, rps) != s) continue;  // only split counts whose spans are all non-empty
     const int64_t ctas = tiles * s;
     const int64_t waves = ceil_div(ctas, slots);
-    const double score = (double)ctas / (double)(waves * slots) - 0.004 * s;
-    if (score > best_score) {
-      best_score = score;
+    const double cost = (double)waves * ((double)rps + 700.0);
+    if (cost < best_cost * (1.0 - 1e-9)) {
+      best_cost = cost;
       best = s;
     }
   }
