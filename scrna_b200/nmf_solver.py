@@ -387,7 +387,10 @@ class NmfSolver:
             total += (nbytes + 255) // 256 * 256
         self.p2p = False
         arena = None
-        if self.comm is not None and getattr(self.comm, "symmetric_arena", None) is not None:
+        # peer-mapped (symmetric) memory only for the opt-in fused gene step: its rendezvous is a collective that costs
+        # tens of milliseconds per solver, which the default NCCL path has no use for
+        if (self.comm is not None and getattr(self.comm, "symmetric_arena", None) is not None
+                and os.environ.get("SCRNA_B200_FUSED", "0") == "1"):
             got = self.comm.symmetric_arena(total, dev)
             if got is not None:
                 arena, ptrs = got
