@@ -87,6 +87,116 @@ pairwise_kernel(const double* __restrict__ X, int64_t ld, int F, int N, double* 
     }
 }
 
+// ---- the Gram G = X^T X on the FP64 tensor cores ---------------------------------------------------------------------
+// pairwise_kernel<DOT> is bound by its shared-memory reads (ncu: 87 % LSU wavefronts, FP64 pipe 34 %): 4 x 4 register
+// tiles need 8 operand doubles per 16 FMA.  A DMMA fragment (mma.sync.m8n8k4.f64) needs 2 per 8 per lane.  CTA =
+// 64 x 128 output tile (8 warps x 32 x 32 as 4 x 4 DMMA tiles), 32 features per stage, the [feature][cell] rows of
+// X staged as they lie in memory with 16-byte cp.async (zero fill past N / F), two stages.  Every output element is
+// the same chain over the features whatever tile it falls in, so a row block (multi-GPU sharding) is bit-identical to
+// the same rows of the full launch.  Symmetric launches skip the tiles entirely below the diagonal; the lower
+// triangle is then copied from the upper one (exactly symmetric result).
+constexpr int GD_K = 32;
+constexpr int GD_TP = 64 + 8;
+constexpr int GD_TQ = 128 + 8;
+constexpr int GD_STAGE = GD_K * (GD_TP + GD_TQ);   // doubles
+
+__device__ __forceinline__ void gd_dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void gd_cp16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+gram_dmma_kernel(const double* __restrict__ X, int64_t ld, int F, int N, double* __restrict__ out, int64_t ldo,
+                 int row_begin, int row_end) {
+  extern __shared__ __align__(16) double gd_smem[];
+  const bool rect = row_begin >= 0;
+  const int i0 = (rect ? row_begin : 0) + blockIdx.y * 64, j0 = blockIdx.x * 128;
+  const int i_end = rect ? row_end : N;
+  if (!rect && j0 + 127 < i0) return;        // entirely below the diagonal: mirrored afterwards
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wr = warp >> 2, wc = warp & 3, lr = lane >> 2, lk = lane & 3;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(gd_smem);
+  const int nk = (F + GD_K - 1) / GD_K;
+  auto issue = [&](int kc) {
+    const uint32_t pb = sbase + (uint32_t)((kc & 1) * GD_STAGE) * 8u, qb = pb + (uint32_t)(GD_K * GD_TP) * 8u;
+    const int f0 = kc * GD_K;
+    for (int e = tid; e < GD_K * 32; e += 256) {            // P: GD_K rows x 64 cells = 32 chunks of 2
+      const int k = e >> 5, ch = e & 31, col = i0 + 2 * ch;
+      const int valid = (f0 + k < F) ? max(0, min(2, N - col)) : 0;
+      gd_cp16(pb + (uint32_t)(k * GD_TP + 2 * ch) * 8u, X + (int64_t)(valid ? f0 + k : 0) * ld + (valid ? col : 0),
+              (uint32_t)valid * 8u);
+    }
+    for (int e = tid; e < GD_K * 64; e += 256) {            // Q: GD_K rows x 128 cells = 64 chunks of 2
+      const int k = e >> 6, ch = e & 63, col = j0 + 2 * ch;
+      const int valid = (f0 + k < F) ? max(0, min(2, N - col)) : 0;
+      gd_cp16(qb + (uint32_t)(k * GD_TQ + 2 * ch) * 8u, X + (int64_t)(valid ? f0 + k : 0) * ld + (valid ? col : 0),
+              (uint32_t)valid * 8u);
+    }
+  };
+  double acc[4][4][2];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+  issue(0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int kc = 0; kc < nk; ++kc) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                   // stage kc landed; stage kc - 1 fully consumed by every warp
+    if (kc + 1 < nk) issue(kc + 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double* P = gd_smem + (kc & 1) * GD_STAGE;
+    const double* Q = P + GD_K * GD_TP;
+#pragma unroll
+    for (int kk = 0; kk < GD_K / 4; ++kk) {
+      const int k = 4 * kk + lk;
+      double a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = P[k * GD_TP + 32 * wr + 8 * u + lr];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) b[v] = Q[k * GD_TQ + 32 * wc + 8 * v + lr];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) gd_dmma(acc[u][v], a[u], b[v]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = i0 + 32 * wr + 8 * u + lr;
+    if (r >= i_end) continue;
+    double* orow = out + (int64_t)(rect ? r - row_begin : r) * ldo;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int c = j0 + 32 * wc + 8 * v + 2 * lk;
+      if (c < N) orow[c] = acc[u][v][0];
+      if (c + 1 < N) orow[c + 1] = acc[u][v][1];
+    }
+  }
+}
+
+// out[i][j] = out[j][i] for i > j (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256)
+mirror_upper_kernel(double* __restrict__ out, int64_t ldo, int N) {
+  __shared__ double t[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;                                  // destination tiles on or below the diagonal
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int y = ty; y < 32; y += 8) {                    // source tile (bj, bi): rows of block bj, columns of block bi
+    const int r = bj * 32 + y, c = bi * 32 + tx;
+    t[y][tx] = (r < N && c < N) ? out[(int64_t)r * ldo + c] : 0.0;
+  }
+  __syncthreads();
+  for (int y = ty; y < 32; y += 8) {
+    const int i = bi * 32 + y, j = bj * 32 + tx;
+    if (i < N && j < N && i > j) out[(int64_t)i * ldo + j] = t[tx][y];
+  }
+}
+
 // column means over the rows of an F x N matrix: mean[j] = (sum_f X[f][j]) / F  (fixed order per column)
 __global__ void col_mean_kernel(const double* __restrict__ X, int64_t ld, int F, int N,
                                 double* __restrict__ mean) {
@@ -181,12 +291,35 @@ transpose_f64_kernel(const double* __restrict__ src, int64_t ld_src, int64_t row
 
 using namespace scrna;
 
+static constexpr size_t GD_SMEM = (size_t)2 * GD_STAGE * sizeof(double);
+// 16-byte staging needs even leading dimension, an aligned base and an even first row of the block
+static bool gram_dmma_ok(const double* X, int64_t ld, int row_begin) {
+  return !(ld & 1) && !(reinterpret_cast<uintptr_t>(X) & 15) && !(row_begin & 1);
+}
+static int gram_dmma_configure() {
+  static bool done = false;
+  if (!done) {
+    if (cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GD_SMEM) != cudaSuccess)
+      return SCRNA_ERR_CUDA;
+    done = true;
+  }
+  return SCRNA_OK;
+}
+
 extern "C" int scrna_pairwise_f64(const double* X, int64_t ld, int F, int N, int op, double* out, int64_t ldo,
                                   void* stream) {
   if (!X || !out || F <= 0 || N <= 0 || ld < N || ldo < N || (op != 0 && op != 1)) return SCRNA_ERR_BADARG;
   const int t = (int)ceil_div(N, PW_TILE);
   if (t > 65535) return SCRNA_ERR_UNSUPPORTED;
   dim3 grid(t, t);
+  if (op == 1 && gram_dmma_ok(X, ld, 0)) {
+    if (int rc = gram_dmma_configure()) return rc;
+    const dim3 gg((unsigned)ceil_div(N, 128), (unsigned)ceil_div(N, 64));
+    gram_dmma_kernel<<<gg, 256, GD_SMEM, (cudaStream_t)stream>>>(X, ld, F, N, out, ldo, -1, -1);
+    const unsigned tm = (unsigned)ceil_div(N, 32);
+    mirror_upper_kernel<<<dim3(tm, tm), 256, 0, (cudaStream_t)stream>>>(out, ldo, N);
+    return last_launch_status();
+  }
   if (op == 0)
     pairwise_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(X, ld, F, N, out, ldo, -1, -1);
   else
@@ -203,6 +336,12 @@ extern "C" int scrna_pairwise_rows_f64(const double* X, int64_t ld, int F, int N
   const int tx = (int)ceil_div(N, PW_TILE), ty = (int)ceil_div(row_end - row_begin, PW_TILE);
   if (tx > 65535 || ty > 65535) return SCRNA_ERR_UNSUPPORTED;
   dim3 grid(tx, ty);
+  if (op == 1 && gram_dmma_ok(X, ld, row_begin)) {
+    if (int rc = gram_dmma_configure()) return rc;
+    const dim3 gg((unsigned)ceil_div(N, 128), (unsigned)ceil_div(row_end - row_begin, 64));
+    gram_dmma_kernel<<<gg, 256, GD_SMEM, (cudaStream_t)stream>>>(X, ld, F, N, out, ldo, row_begin, row_end);
+    return last_launch_status();
+  }
   if (op == 0)
     pairwise_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(X, ld, F, N, out, ldo, row_begin, row_end);
   else
