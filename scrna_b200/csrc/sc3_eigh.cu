@@ -319,6 +319,20 @@ eh_syr2k_kernel(double* __restrict__ A, int64_t ld, int n, int lo, int nb, const
   // only the upper triangle by 128-aligned blocks (columns in a block >= the row's block) is read again (k1 reads
   // row c to the right of the diagonal, eh_symv_upper_kernel tiles J >= I): tiles entirely left of it are skipped
   if (upper_only && s0 + 127 < (r0 / EH_SB) * EH_SB) return;
+  // the tile of A goes straight into the accumulators (its loads fly while the operands are staged) and the column
+  // operand is staged negated: acc = A - V^T W - W^T V comes out of the DMMA chain, the epilogue only stores
+  double acc[4][4][2];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = r0 + 32 * wr + 8 * u + lr;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int s = s0 + 32 * wc + 8 * v + 2 * lk;
+      const double* p = A + (int64_t)r * ld + s;
+      acc[u][v][0] = (r < n && s < n) ? p[0] : 0.0;
+      acc[u][v][1] = (r < n && s + 1 < n) ? p[1] : 0.0;
+    }
+  }
   for (int e = tid; e < 64 * 64; e += 256) {
     const int k = e >> 6, r = e & 63;
     const double* src = (k < 32 ? Vp + (int64_t)k * n : Wp + (int64_t)(k - 32) * n);
@@ -327,14 +341,9 @@ eh_syr2k_kernel(double* __restrict__ A, int64_t ld, int n, int lo, int nb, const
   for (int e = tid; e < 64 * 128; e += 256) {
     const int k = e >> 7, s = e & 127;
     const double* src = (k < 32 ? Wp + (int64_t)k * n : Vp + (int64_t)(k - 32) * n);
-    Q[k * EH_TQ + s] = (k % 32 < nb && s0 + s < n) ? src[s0 + s] : 0.0;
+    Q[k * EH_TQ + s] = (k % 32 < nb && s0 + s < n) ? -src[s0 + s] : 0.0;
   }
   __syncthreads();
-  double acc[4][4][2];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 #pragma unroll 4
   for (int kk = 0; kk < 16; ++kk) {
     const int k = 4 * kk + lk;
@@ -356,8 +365,8 @@ eh_syr2k_kernel(double* __restrict__ A, int64_t ld, int n, int lo, int nb, const
     for (int v = 0; v < 4; ++v) {
       const int s = s0 + 32 * wc + 8 * v + 2 * lk;
       double* p = A + (int64_t)r * ld + s;
-      if (s < n) p[0] -= acc[u][v][0];
-      if (s + 1 < n) p[1] -= acc[u][v][1];
+      if (s < n) p[0] = acc[u][v][0];
+      if (s + 1 < n) p[1] = acc[u][v][1];
     }
   }
 }
