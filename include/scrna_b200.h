@@ -457,6 +457,12 @@ int scrna_stebz_top_f64(const double* d, const double* e, int n, int c, double g
 int scrna_stein_f64(const double* d, const double* e, int n, int c, const double* lam, double tnorm, double* work,
                     int8_t* iwork, double* X, int iters, void* stream);
 int scrna_ormtr_f64(const double* A, int64_t ld, int n, const double* tau, double* ZT, int c, void* stream);
+/* The same in blocks of 32 reflectors (compact WY: two FP64 tensor-core GEMMs per block instead of 32 dot / axpy
+ * passes); work: scrna_ormtr_work_elems(n, c) doubles; needs n even and ZT 16-byte aligned, else
+ * SCRNA_ERR_UNSUPPORTED (use scrna_ormtr_f64). */
+int64_t scrna_ormtr_work_elems(int n, int c);
+int scrna_ormtr_blocked_f64(const double* A, int64_t ld, int n, const double* tau, double* ZT, int c, double* work,
+                            void* stream);
 
 #ifdef __cplusplus
 }

@@ -104,6 +104,8 @@ _SIGNATURES = {
     "scrna_stebz_top_f64": [c_ptr, c_ptr, c_int, c_int, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr],
     "scrna_stein_f64": [c_ptr, c_ptr, c_int, c_int, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_int, c_ptr],
     "scrna_ormtr_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_ptr],
+    "scrna_ormtr_work_elems": [c_int, c_int],
+    "scrna_ormtr_blocked_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr],
     "scrna_gather_scaled_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr],
     "scrna_gather_rows_scaled_f64": [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr],
     "scrna_kta_blocks": [],
@@ -146,12 +148,13 @@ _VALUE_RETURNING = {"scrna_abi_version", "scrna_nmf_xht_splits", "scrna_nmf_wtx_
                     "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems", "scrna_kta_blocks",
                     "scrna_nmf_h_supported", "scrna_nmf_h_nb", "scrna_nmf_h_shadow_elems", "scrna_nmf_wtx_h_splits",
                     "scrna_f16_panel_rows", "scrna_f16_panel_elems", "scrna_nmf_h_groups", "scrna_nmf_step_groups", "scrna_sytrd_work_elems",
-                    "scrna_lloyd_batched_supported", "scrna_lloyd_batched_work_elems", "scrna_km_prepare_work_elems"}
+                    "scrna_lloyd_batched_supported", "scrna_lloyd_batched_work_elems", "scrna_km_prepare_work_elems",
+                    "scrna_ormtr_work_elems"}
 
 
 _RETURNS_I64 = {"scrna_sytrd_work_elems", "scrna_nmf_tc_shadow_elems", "scrna_nmf_h_shadow_elems", "scrna_f16_panel_rows", "scrna_f16_panel_elems",
                 "scrna_nmf_h_groups", "scrna_bjacobi_work_elems", "scrna_lloyd_sums_work_elems",
-                "scrna_lloyd_batched_work_elems", "scrna_km_prepare_work_elems"}
+                "scrna_lloyd_batched_work_elems", "scrna_km_prepare_work_elems", "scrna_ormtr_work_elems"}
 
 
 class ScrnaError(RuntimeError):

@@ -605,6 +605,210 @@ eh_backtransform_smem_kernel(const double* __restrict__ A, int64_t ld, int n, co
   }
 }
 
+// ---- blocked back-transformation (compact WY, LAPACK dlarft / dlarfb restated) -------------------------------------
+// 32 consecutive reflectors H_j ... H_{j+31} = I - V T V^T (T upper triangular from the Gram of the reflectors), so a
+// block is applied to all vectors by two GEMMs on the FP64 tensor cores instead of 32 dot / axpy passes:
+//      W1 = ZT . V        (vectors x 32, reduction over the rows: split into row chunks, partials added in order)
+//      W2 = W1 . T^T
+//      ZT -= W2 . V^T     (rank-32 update, the tile of ZT loaded straight into the DMMA accumulators)
+// V[p][r] = A[j + p][r] for r > j + p (leading 1 stored), else 0.
+constexpr int OB = 32;             // reflectors per block
+constexpr int OB_RC = 2048;        // rows per split of the W1 reduction
+constexpr int OB_KS = 16;          // rows per stage of the W1 kernel
+constexpr int OB_SP = OB_KS + 4;   // its shared-memory pitch
+
+__device__ __forceinline__ double ob_v(const double* __restrict__ A, int64_t ld, int j, int nb, int p, int r, int n) {
+  return (p < nb && r > j + p && r < n) ? A[(int64_t)(j + p) * ld + r] : 0.0;
+}
+
+// T of every block: grid = blocks
+__global__ void __launch_bounds__(256)
+ob_t_kernel(const double* __restrict__ A, int64_t ld, int n, const double* __restrict__ tau, double* __restrict__ Tg) {
+  __shared__ double sV[OB][65];
+  __shared__ double S[OB][OB + 1];
+  __shared__ double T[OB][OB + 1];
+  const int j = blockIdx.x * OB, nref = n - 2, nb = min(OB, nref - j);
+  const int tid = threadIdx.x;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int r0 = j + 1; r0 < n; r0 += 64) {
+    __syncthreads();
+    for (int e = tid; e < OB * 64; e += 256) {
+      const int p = e >> 6, rr = e & 63;
+      sV[p][rr] = ob_v(A, ld, j, nb, p, r0 + rr, n);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid * 4 + e, p = idx >> 5, i = idx & 31;
+      double a = acc[e];
+#pragma unroll 8
+      for (int rr = 0; rr < 64; ++rr) a = fma(sV[p][rr], sV[i][rr], a);
+      acc[e] = a;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int idx = tid * 4 + e;
+    S[idx >> 5][idx & 31] = acc[e];
+  }
+  for (int e = tid; e < OB * (OB + 1); e += 256) (&T[0][0])[e] = 0.0;
+  __syncthreads();
+  if (tid < nb) {               // row a of T depends on its own earlier entries only
+    const int a = tid;
+    T[a][a] = tau[j + a];
+    for (int i = a + 1; i < nb; ++i) {
+      double sum = 0.0;
+      for (int q = a; q < i; ++q) sum = fma(T[a][q], S[q][i], sum);
+      T[a][i] = -tau[j + i] * sum;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < OB * OB; e += 256) Tg[(int64_t)blockIdx.x * OB * OB + e] = T[e >> 5][e & 31];
+}
+
+// W1 partials: grid (ceil(c / 64), row chunks); 128 threads; out W1p[(chunk * cpad + vector) * 32 + p]
+__global__ void __launch_bounds__(128)
+ob_w1_kernel(const double* __restrict__ A, int64_t ld, int n, int j, int nb, int rbase, const double* __restrict__ ZT,
+             int c, int cpad, double* __restrict__ W1p) {
+  __shared__ __align__(16) double zs[2][64 * OB_SP];
+  __shared__ __align__(16) double vs[2][OB * OB_SP];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lk = lane & 3;
+  const int v0 = blockIdx.x * 64;
+  const int r_lo = rbase + blockIdx.y * OB_RC, r_hi = min(n, r_lo + OB_RC);
+  const uint32_t zs_a = (uint32_t)__cvta_generic_to_shared(&zs[0][0]);
+  const int nk = (r_hi - r_lo + OB_KS - 1) / OB_KS;
+  auto issue = [&](int kc) {
+    const int st = kc & 1, r0 = r_lo + kc * OB_KS;
+    for (int e = tid; e < 64 * (OB_KS / 2); e += 128) {
+      const int row = e >> 3, ch = e & 7, r = r0 + 2 * ch, v = v0 + row;
+      const int valid = (v < c) ? max(0, min(2, r_hi - r)) : 0;
+      const uint32_t dst = zs_a + (uint32_t)((st * 64 + row) * OB_SP + 2 * ch) * 8u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
+                   "l"(ZT + (int64_t)(valid ? v : 0) * n + (valid ? r : 0)), "r"((uint32_t)valid * 8u)
+                   : "memory");
+    }
+    for (int e = tid; e < OB * OB_KS; e += 128) {
+      const int p = e >> 4, rr = e & 15, r = r0 + rr;
+      vs[st][p * OB_SP + rr] = r < r_hi ? ob_v(A, ld, j, nb, p, r, n) : 0.0;
+    }
+  };
+  double acc[2][4][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[u][t][0] = acc[u][t][1] = 0.0;
+  issue(0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int kc = 0; kc < nk; ++kc) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (kc + 1 < nk) issue(kc + 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double* xt = &zs[kc & 1][(warp * 16 + lr) * OB_SP + lk];
+    const double* ct = &vs[kc & 1][lr * OB_SP + lk];
+#pragma unroll
+    for (int ks = 0; ks < OB_KS / 4; ++ks) {
+      const double a0 = xt[4 * ks], a1 = xt[8 * OB_SP + 4 * ks];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const double b = ct[t * 8 * OB_SP + 4 * ks];
+        eh_dmma(acc[0][t], a0, b);
+        eh_dmma(acc[1][t], a1, b);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int v = v0 + warp * 16 + u * 8 + lr;
+    if (v >= c) continue;
+    double* o = W1p + ((int64_t)blockIdx.y * cpad + v) * OB;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      o[t * 8 + 2 * lk] = acc[u][t][0];
+      o[t * 8 + 2 * lk + 1] = acc[u][t][1];
+    }
+  }
+}
+
+// W2k[q][vector] = sum_p (sum_chunks W1p[chunk][vector][p]) T[q][p]; 8 vectors per CTA of 256 threads
+__global__ void __launch_bounds__(256)
+ob_w2_kernel(const double* __restrict__ W1p, int nchunks, int c, int cpad, const double* __restrict__ Tb,
+             double* __restrict__ W2k) {
+  __shared__ double w1[8][OB + 1];
+  __shared__ double T[OB][OB + 1];
+  const int tid = threadIdx.x, vl = tid >> 5, p = tid & 31;
+  const int v = blockIdx.x * 8 + vl;
+  for (int e = tid; e < OB * OB; e += 256) T[e >> 5][e & 31] = Tb[e];
+  double s = 0.0;
+  if (v < c)
+    for (int ch = 0; ch < nchunks; ++ch) s += W1p[((int64_t)ch * cpad + v) * OB + p];   // fixed order
+  w1[vl][p] = s;
+  __syncthreads();
+  const int q = p;
+  double o = 0.0;
+#pragma unroll 8
+  for (int pp = 0; pp < OB; ++pp) o = fma(w1[vl][pp], T[q][pp], o);
+  if (v < cpad) W2k[(int64_t)q * cpad + v] = v < c ? o : 0.0;
+}
+
+// ZT[vector][r] -= sum_q W2k[q][vector] V[q][r]: CTA = 64 vectors x 128 rows, K = 32
+__global__ void __launch_bounds__(256)
+ob_update_kernel(const double* __restrict__ A, int64_t ld, int n, int j, int nb, int rbase, double* __restrict__ ZT,
+                 int c, int cpad, const double* __restrict__ W2k) {
+  extern __shared__ __align__(16) double ob_smem[];
+  double* P = ob_smem;                 // [q][vector < 64]
+  double* Q = P + OB * EH_TP;          // [q][row < 128], negated
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wr = warp >> 2, wc = warp & 3, lr = lane >> 2, lk = lane & 3;
+  const int v0 = blockIdx.y * 64, r0 = rbase + blockIdx.x * 128;
+  double acc[4][4][2];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int v = v0 + 32 * wr + 8 * u + lr;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int r = r0 + 32 * wc + 8 * w + 2 * lk;
+      const double* zp = ZT + (int64_t)v * n + r;
+      acc[u][w][0] = (v < c && r < n) ? zp[0] : 0.0;
+      acc[u][w][1] = (v < c && r + 1 < n) ? zp[1] : 0.0;
+    }
+  }
+  for (int e = tid; e < OB * 64; e += 256) {
+    const int q = e >> 6, vv = e & 63;
+    P[q * EH_TP + vv] = (v0 + vv < cpad) ? W2k[(int64_t)q * cpad + v0 + vv] : 0.0;
+  }
+  for (int e = tid; e < OB * 128; e += 256) {
+    const int q = e >> 7, rr = e & 127;
+    Q[q * EH_TQ + rr] = -ob_v(A, ld, j, nb, q, r0 + rr, n);
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int kk = 0; kk < OB / 4; ++kk) {
+    const int k = 4 * kk + lk;
+    double a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = P[k * EH_TP + 32 * wr + 8 * u + lr];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) b[u] = Q[k * EH_TQ + 32 * wc + 8 * u + lr];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) eh_dmma(acc[u][w], a[u], b[w]);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int v = v0 + 32 * wr + 8 * u + lr;
+    if (v >= c) continue;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int r = r0 + 32 * wc + 8 * w + 2 * lk;
+      double* zp = ZT + (int64_t)v * n + r;
+      if (r < n) zp[0] = acc[u][w][0];
+      if (r + 1 < n) zp[1] = acc[u][w][1];
+    }
+  }
+}
+
 }  // namespace scrna
 
 using namespace scrna;
@@ -671,6 +875,46 @@ extern "C" int scrna_sytrd_f64(double* A, int64_t ld, int n, double* d, double* 
   cudaMemcpyAsync(e + n - 2, A + (int64_t)(n - 2) * ld + (n - 1), sizeof(double), cudaMemcpyDeviceToDevice, st);
   cudaMemcpyAsync(d + n - 1, A + (int64_t)(n - 1) * ld + (n - 1), sizeof(double), cudaMemcpyDeviceToDevice, st);
   cudaMemsetAsync(tau + n - 2, 0, 2 * sizeof(double), st);
+  return last_launch_status();
+}
+
+// work of the blocked back-transformation: T of every block + W1 partials + W2
+extern "C" int64_t scrna_ormtr_work_elems(int n, int c) {
+  if (n < 3 || c < 1) return SCRNA_ERR_BADARG;
+  const int64_t nblocks = ceil_div(n - 2, OB), cpad = ceil_div(c, 64) * 64;
+  const int64_t chunks = ceil_div(n, OB_RC) + 1;
+  return nblocks * OB * OB + chunks * cpad * OB + (int64_t)OB * cpad;
+}
+
+// ZT (c x n, one vector per row, leading dimension n) <- Q z for every row, in blocks of 32 reflectors (compact WY, two
+// DMMA GEMMs per block).  Needs n even and ZT 16-byte aligned (else SCRNA_ERR_UNSUPPORTED: use scrna_ormtr_f64).
+extern "C" int scrna_ormtr_blocked_f64(const double* A, int64_t ld, int n, const double* tau, double* ZT, int c,
+                                       double* work, void* stream) {
+  if (!A || !tau || !ZT || !work || n < 3 || ld < n || c <= 0) return SCRNA_ERR_BADARG;
+  if ((n & 1) || (reinterpret_cast<uintptr_t>(ZT) & 15)) return SCRNA_ERR_UNSUPPORTED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nref = n - 2, nblocks = (int)ceil_div(nref, OB), cpad = (int)(ceil_div(c, 64) * 64);
+  double* Tg = work;
+  double* W1p = Tg + (int64_t)nblocks * OB * OB;
+  double* W2k = W1p + (ceil_div(n, OB_RC) + 1) * (int64_t)cpad * OB;
+  const size_t smem_u = (size_t)OB * (EH_TP + EH_TQ) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(ob_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u) != cudaSuccess)
+      return SCRNA_ERR_CUDA;
+    attr = true;
+  }
+  ob_t_kernel<<<nblocks, 256, 0, st>>>(A, ld, n, tau, Tg);
+  for (int bk = nblocks - 1; bk >= 0; --bk) {
+    const int j = bk * OB, nb = nref - j < OB ? nref - j : OB;
+    const int rbase = ((j + 1) / 16) * 16;                 // first row that can be non-zero, aligned down to a stage
+    const int nchunks = (int)ceil_div(n - rbase, OB_RC);
+    ob_w1_kernel<<<dim3((unsigned)ceil_div(c, 64), (unsigned)nchunks), 128, 0, st>>>(A, ld, n, j, nb, rbase, ZT, c, cpad,
+                                                                                    W1p);
+    ob_w2_kernel<<<(unsigned)(cpad / 8), 256, 0, st>>>(W1p, nchunks, c, cpad, Tg + (int64_t)bk * OB * OB, W2k);
+    ob_update_kernel<<<dim3((unsigned)ceil_div(n - rbase, 128), (unsigned)ceil_div(c, 64)), 256, smem_u, st>>>(
+        A, ld, n, j, nb, rbase, ZT, c, cpad, W2k);
+  }
   return last_launch_status();
 }
 

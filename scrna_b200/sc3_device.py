@@ -8,6 +8,8 @@ few scalars per k-means iteration / Jacobi sweep for the stop rules, and draws n
 import contextlib
 import time
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -234,6 +236,16 @@ class Sc3Ops:
         self._last = (W, od, inv[order[:c]], vals[order][:c])   # for rebuilt_matrix()
         return V, vals[order]
 
+    def _ormtr(self, A, n, tau, ZT, c):
+        """Rows of ZT (c x n) <- Q z with Q from scrna_sytrd_f64's reflectors: in blocks of 32 reflectors as two
+        FP64 tensor-core GEMMs per block (compact WY) when n is even, else reflector by reflector."""
+        if n % 2 == 0 and os.environ.get("SCRNA_B200_ORMTR", "blocked") != "legacy":
+            work = self.empty(_lib.call("scrna_ormtr_work_elems", int(n), int(c)))
+            self._call("scrna_ormtr_blocked_f64", A, n, n, tau, ZT, int(c), work, self._s(),
+                       launches=1 + 3 * ((n - 2 + 31) // 32))
+        else:
+            self._call("scrna_ormtr_f64", A, n, n, tau, ZT, int(c), self._s())
+
     def _rsv_eigh(self, M, components, comm=None):
         """Leading `components` eigenpairs of A = M^T M (sc3_eigh.cu).  The host does O(n) bookkeeping only:
         Gershgorin bounds of the tridiagonal matrix and dstein's separation of numerically coincident eigenvalues."""
@@ -282,13 +294,13 @@ class Sc3Ops:
         self._call("scrna_transpose_f64", X, c, n, c, ZT, n, self._s())
         with self._stage("svd.back_transform"):
             if comm is None or comm.world <= 1:
-                self._call("scrna_ormtr_f64", A, n, n, tau, ZT, c, self._s())
+                self._ormtr(A, n, tau, ZT, c)
             else:   # the vectors are independent: each rank back-transforms a block of them, then all-gather
                 from .nmf_solver import shard_bounds
                 bounds = [shard_bounds(c, comm.world, r) for r in range(comm.world)]
                 c0, c1 = bounds[comm.rank]
                 if c1 > c0:
-                    self._call("scrna_ormtr_f64", A, n, n, tau, ZT[c0:c1], c1 - c0, self._s())
+                    self._ormtr(A, n, tau, ZT[c0:c1], c1 - c0)
                 comm.all_gather_rows(ZT, bounds)
         V = X
         self._call("scrna_transpose_f64", ZT, n, c, n, V, c, self._s())

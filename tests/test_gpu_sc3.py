@@ -108,6 +108,27 @@ def test_tridiagonalisation_preserves_the_spectrum(ops):
     np.testing.assert_allclose(Q @ T @ Q.T, A, rtol=0, atol=1e-9 * np.abs(A).max())
 
 
+@pytest.mark.parametrize("n,c", [(518, 37), (2050, 144), (64, 5)])
+def test_blocked_back_transformation_equals_the_reflector_walk(ops, n, c):
+    """scrna_ormtr_blocked_f64 (32 reflectors at a time as I - V T V^T: two DMMA GEMMs per block) against
+    scrna_ormtr_f64 (one reflector at a time) on the reflectors of a tridiagonalised matrix, and Q orthogonal."""
+    import scrna_b200._lib as L
+    rng = np.random.RandomState(n)
+    B = rng.randn(n, n)
+    Ad = ops.to_device(B @ B.T + np.diag(rng.rand(n)))
+    d, e, tau = ops.empty(n), ops.zeros(n), ops.empty(n)
+    ops._call("scrna_sytrd_f64", Ad, n, n, d, e, tau, ops.empty(L.call("scrna_sytrd_work_elems", n)), ops._s())
+    Z = rng.randn(c, n)
+    Z /= np.linalg.norm(Z, axis=1, keepdims=True)
+    Za, Zb = ops.to_device(Z.copy()), ops.to_device(Z.copy())
+    ops._call("scrna_ormtr_f64", Ad, n, n, tau, Za, c, ops._s())
+    ops._call("scrna_ormtr_blocked_f64", Ad, n, n, tau, Zb, c, ops.empty(L.call("scrna_ormtr_work_elems", n, c)), ops._s())
+    a, b = Za.cpu().numpy(), Zb.cpu().numpy()
+    np.testing.assert_allclose(b, a, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(np.linalg.norm(b, axis=1), 1.0, rtol=0, atol=1e-12)   # Q is orthogonal
+    np.testing.assert_allclose(b @ b.T, Z @ Z.T, rtol=0, atol=1e-12)
+
+
 def test_rank_average_more_genes_than_one_shared_memory_chunk(ops):
     """Round 1 returned UNSUPPORTED above 28 160 genes: the ranks are now counted against the gene vector in chunks."""
     rng = np.random.RandomState(2)
