@@ -371,29 +371,52 @@ eh_syr2k_kernel(double* __restrict__ A, int64_t ld, int n, int lo, int nb, const
   }
 }
 
-// ---- eigenvalues: the `c` largest by bisection on Sturm counts (LAPACK dstebz idea), one thread each ---------------
-__global__ void eh_bisect_kernel(const double* __restrict__ d, const double* __restrict__ e, int n, int c, double gl,
-                                 double gu, double pivmin, double* __restrict__ lam) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;   // j-th largest
+// ---- eigenvalues: the `c` largest by bisection on Sturm counts (LAPACK dstebz idea).  One WARP per eigenvalue: the 32
+// lanes count at 32 interior points of the bracket at once (a 33-section step narrows it 33x for the price of one
+// n-term recurrence), then plain bisection finishes the last few ulps with the original stopping rule.
+__device__ __forceinline__ int eh_sturm_count(const double* __restrict__ d, const double* __restrict__ e, int n, double x,
+                                              double pivmin) {
+  int cnt = 0;                                         // eigenvalues < x
+  double q = d[0] - x;
+  if (fabs(q) < pivmin) q = -pivmin;
+  cnt += q < 0.0;
+  for (int k = 1; k < n; ++k) {
+    const double ek = e[k - 1];
+    q = d[k] - x - ek * ek / q;
+    if (fabs(q) < pivmin) q = -pivmin;
+    cnt += q < 0.0;
+  }
+  return cnt;
+}
+
+__global__ void __launch_bounds__(128)
+eh_bisect_kernel(const double* __restrict__ d, const double* __restrict__ e, int n, int c, double gl,
+                 double gu, double pivmin, double* __restrict__ lam) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // j-th largest, uniform over the warp
   if (j >= c) return;
+  const int lane = threadIdx.x & 31;
   const int want = n - 1 - j;                            // ascending index of the wanted eigenvalue
-  double lo = gl, hi = gu;
+  double lo = gl, hi = gu;                               // invariant: count(lo) <= want < count(hi)
+  for (int it = 0; it < 40; ++it) {
+    const double w = (hi - lo) / 33.0;
+    const double x0 = lo + w, x31 = lo + 32.0 * w;
+    if (!(w > 0.0) || x0 <= lo || x31 >= hi) break;       // the bracket is a few ulps wide: finish by bisection
+    const double x = lo + (double)(lane + 1) * w;
+    const int cnt = eh_sturm_count(d, e, n, x, pivmin);
+    const unsigned below = __ballot_sync(0xffffffffu, cnt <= want);
+    const int m = below == 0xffffffffu ? 32 : __ffs(~below) - 1;   // leading lanes whose point is still a lower bound
+    const double nlo = m > 0 ? lo + (double)m * w : lo;
+    const double nhi = m < 32 ? lo + (double)(m + 1) * w : hi;
+    lo = nlo;
+    hi = nhi;
+  }
   for (int it = 0; it < 200; ++it) {
     const double mid = 0.5 * (lo + hi);
     if (mid <= lo || mid >= hi) break;
-    int cnt = 0;                                         // eigenvalues < mid
-    double q = d[0] - mid;
-    if (fabs(q) < pivmin) q = -pivmin;
-    cnt += q < 0.0;
-    for (int k = 1; k < n; ++k) {
-      const double ek = e[k - 1];
-      q = d[k] - mid - ek * ek / q;
-      if (fabs(q) < pivmin) q = -pivmin;
-      cnt += q < 0.0;
-    }
+    const int cnt = eh_sturm_count(d, e, n, mid, pivmin);   // every lane the same value
     if (cnt <= want) lo = mid; else hi = mid;
   }
-  lam[j] = 0.5 * (lo + hi);
+  if (lane == 0) lam[j] = 0.5 * (lo + hi);
 }
 
 // ---- eigenvectors of T by inverse iteration (LAPACK dstein with dlagtf / dlagts), one thread per vector; the work
@@ -921,8 +944,8 @@ extern "C" int scrna_ormtr_blocked_f64(const double* A, int64_t ld, int n, const
 extern "C" int scrna_stebz_top_f64(const double* d, const double* e, int n, int c, double gl, double gu, double pivmin,
                                    double* lam, void* stream) {
   if (!d || !e || !lam || n < 2 || c < 1 || c > n || !(gu > gl)) return SCRNA_ERR_BADARG;
-  eh_bisect_kernel<<<(unsigned)ceil_div(c, 32), 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d, e, n, c, gl, gu,
-                                                                                               pivmin, lam);
+  eh_bisect_kernel<<<(unsigned)ceil_div(c, 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d, e, n, c, gl, gu,
+                                                                                              pivmin, lam);
   return last_launch_status();
 }
 
