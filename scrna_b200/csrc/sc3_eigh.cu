@@ -11,14 +11,15 @@
 //      v = Q z                        2 n^2 c        the n - 2 reflectors applied to c vectors
 // Squaring costs accuracy only where it does not matter here: eigenvector errors are eps |A| / gap, and the kept
 // eigenvalues (sigma^2 from 2.4e6 down to ~9e2 at n = 20 000) have gaps ~1e0, i.e. 1e-10 -- two digits inside the
-// 1e-8 the pipeline is held to.  Used for n >= 2048 (Sc3Ops.right_singular_vectors); smaller matrices, and with them
+// 1e-8 the pipeline is held to.  Used for n >= 6000 (Sc3Ops.right_singular_vectors); smaller matrices, and with them
 // every golden-vector parity test, stay on the Jacobi solver.
 //
 // Tridiagonalisation (LAPACK dsytrd / dlatrd, lower variant, restated for the device).  A is kept FULL and symmetric
 // (both triangles), row-major, so "column c" is read as the contiguous row c.  Panels of 32 columns; per column c:
 //   k1  x = A[c][c+1:] - (panel corrections)                                 -> unscaled reflector, partial |x|^2
 //   k2  beta, tau, scale (one warp);  d[c], e[c], tau[c]
-//   k3  y = A22 . v                  (the HBM-bound symmetric matrix-vector product over the trailing matrix)
+//   k3  y = A22 . v                  (the HBM-bound symmetric matrix-vector product over the trailing matrix; reads one
+//                                     triangle by 128 x 128 tiles, eh_symv_upper_kernel)
 //   k4  t1 = Wp^T v, t2 = Vp^T v     (panel corrections of y), v stored: Vp[i] and, for the back-transformation, A[c]
 //   k5  w' = y - Vp^T t1 - Wp^T t2,  partial w'.v
 //   k6  w = tau w' - (tau^2 (w'.v) / 2) v  -> Wp[i]
