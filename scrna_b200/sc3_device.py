@@ -22,6 +22,19 @@ def kmeans_draw_count(k):
     return 1 + (k - 1) * trials, trials
 
 
+def uniform_choice_cdf(n):
+    """cdf of RandomState.choice(n, p=full(n, 1/n)): numpy accumulates p sequentially and normalises by the last entry
+    (numpy/random/mtrand.pyx, `choice`); sklearn's k-means++ draws its first centre this way (_kmeans.py:231)."""
+    cdf = np.full(n, 1.0 / n).cumsum()
+    cdf /= cdf[-1]
+    return cdf
+
+
+def first_centres(cdf, uniforms):
+    """choice's index for each uniform draw: searchsorted(cdf, u, side='right'), clipped like the device kernel."""
+    return np.minimum(np.searchsorted(cdf, uniforms, side="right"), cdf.size - 1)
+
+
 def same_clustering(l1, l2, k):
     """sklearn _is_same_clustering (_k_means_common.pyx:314-328)."""
     mapping = np.full(k, -1, dtype=np.int64)
@@ -382,10 +395,9 @@ class Sc3Ops:
         # searchsorted(cdf, u, side='right') on the sequentially accumulated cdf -- NumPy's own arithmetic, once per n
         cdf = self._uniform_cdf.get(n)
         if cdf is None:
-            cdf = np.full(n, 1.0 / n).cumsum()
-            cdf /= cdf[-1]
+            cdf = uniform_choice_cdf(n)
             self._uniform_cdf = {n: cdf}
-        firsts = np.minimum(np.searchsorted(cdf, draws[: R * per: per], side="right"), n - 1)
+        firsts = first_centres(cdf, draws[: R * per: per])
         # k-means++ of all restarts in one launch sequence (the restart is a grid dimension of every kernel)
         firsts_d = t.from_numpy(firsts.astype(np.int32)).to(self.dev)
         self._call("scrna_kmeans_pp_batched", X, ld, n, d, xsq, k, R, firsts_d, U, trials, closest, cand_dist, cums,
