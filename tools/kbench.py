@@ -71,13 +71,15 @@ def main():
             eb = 2 if slv.half else 4
             name = "tcgen05 f16" if slv.half else "tcgen05 tf32"
             med, best = timeit(lambda: slv._sweep_X(None))
+            xbytes = (slv.Xs.rows_pad * slv.Xs.npanels * 256 * 2) if slv.half else g * ldx * 4   # bytes one sweep streams
             out.append(dict(kernel="sweep_X(%s)" % name, k=k, kp=kp, exact=slv.half or slv.tc_flags == 32, nsplit=slv.SB,
-                            ms=med, best_ms=best, gbs=g * ldx * eb / med / 1e6))
+                            ms=med, best_ms=best, gbs=xbytes / med / 1e6))
             print(out[-1], flush=True)
             XT = slv.XT
             med, best = timeit(lambda: slv._sweep_XT(None))
+            xtbytes = (XT.rows_pad * XT.npanels * 256 * 2) if slv.half else XT.g * XT.ldx * 4
             out.append(dict(kernel="sweep_XT(%s)" % name, k=k, kp=kp, exact=slv.half or slv.tc_flags == 32, nsplit=slv.SA,
-                            ms=med, best_ms=best, gbs=XT.g * XT.ldx * eb / med / 1e6))
+                            ms=med, best_ms=best, gbs=xtbytes / med / 1e6))
             print(out[-1], flush=True)
             sb_list, sa_list = [], []
             if slv.half:
